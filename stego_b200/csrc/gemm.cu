@@ -1,0 +1,327 @@
+// tcgen05 / TMA / TMEM GEMM for the STEGO hot path (sm_100a).
+//
+//   out[M,N] = act(A[M,K] . B[N,K]^T + bias[N]) + residual[M,N]
+//
+// used for every dense contraction on the path that is a plain GEMM:
+//   * DINO ViT linears  (reference: src/dino/vision_transformer.py:58-62 Mlp, :80,:88 Attention qkv/proj,
+//                        :127-131 PatchEmbed as an im2col GEMM)
+//   * segmentation head (reference: src/modules.py:73-81 cluster1/cluster2 1x1 convs) forward,
+//     dgrad (B operand MN-major) and wgrad (both operands MN-major, split-K + fp32 atomics).
+//
+// Structure: persistent CTAs (one per SM), 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM, 2 buffers)
+//   warps 2..5  epilogue       (tcgen05.ld TMEM->regs, bias/GELU/ReLU/residual, vectorised global stores)
+// Operand tiles are 128 x 64 (A) and BN x 64 (B) bf16; accumulation fp32.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace stego {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;        // logical GEMM sizes; K is the reduction length
+  int splits;         // split-K factor (>=1); every split owns >= 1 k-block
+  int kb_per_split;   // k-blocks per split
+  void* out;          // [M or remapped rows][ldo]
+  int ldo;
+  int out_bf16;       // 1: bf16 output, 0: fp32 output
+  const float* bias;  // [N] or null
+  int act;            // 0 none, 1 GELU(erf), 2 ReLU
+  const float* residual;  // fp32 [rows][ldr] or null (may alias out)
+  int ldr;
+  int row_div;        // >0: patch-embed mode: out_row = r + r/row_div + 1, residual row = r % row_div + 1
+  int atomic;         // 1: fp32 atomicAdd into out (split-K)
+  int vec_ok;         // host-verified 16-byte alignment of out/residual rows
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int kStages, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+  constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "BN must be 128 or 256");
+  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_kb = p.K / GEMM_BK;
+  const int total_tiles = tiles_m * tiles_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t % p.splits;
+        const int tn = (t / p.splits) % tiles_n;
+        const int tm = t / (p.splits * tiles_n);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, tm * GEMM_BM);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < GEMM_BM / 64; ++blk)
+              tma_load_2d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < BN / 64; ++blk)
+              tma_load_2d(sb + blk * 8192, &tmB, &full_bar[stage], tn * BN + blk * 64, kb * GEMM_BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // K-major: advance 16 elements = 32 B inside the 128-B swizzle row.
+            // MN-major: advance 16 k-rows = 2048 B; 64-wide M/N blocks are 8192 B apart (LBO).
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tn = (t / p.splits) % tiles_n;
+      const int tm = t / (p.splits * tiles_n);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = tm * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      int out_row = row, res_row = row;
+      if (p.row_div > 0) {
+        out_row = row + row / p.row_div + 1;
+        res_row = row % p.row_div + 1;
+      }
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tn * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the previous store
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        const bool full = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+        }
+        if (p.atomic) {
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) atomicAdd(o + j, x[j]);
+          continue;
+        }
+        if (full && p.vec_ok) {
+          if (p.residual != nullptr) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(res_row) * p.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = r4[j];
+              x[4 * j + 0] += r.x; x[4 * j + 1] += r.y; x[4 * j + 2] += r.z; x[4 * j + 3] += r.w;
+            }
+          }
+          if (p.out_bf16) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+              w.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+              w.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+              w.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+              o[j] = w;
+            }
+          } else {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+              float y = x[j];
+              if (p.residual != nullptr) y += p.residual[static_cast<size_t>(res_row) * p.ldr + col0 + j];
+              if (p.out_bf16)
+                reinterpret_cast<bf16*>(p.out)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = __float2bfloat16_rn(y);
+              else
+                reinterpret_cast<float*>(p.out)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = y;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int kStages, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 256;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
+    configured = true;
+  }
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+  STEGO_CHECK_LAUNCH("gemm_bf16_kernel launch");
+  return STEGO_OK;
+}
+
+}  // namespace stego
+
+using namespace stego;
+
+// C-ABI: see include/stego_b200.h for the contract.
+extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
+                               int N, int K, void* out, int ldo, int out_bf16, const float* bias, int act,
+                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(A && B && out, "stego_gemm_bf16: null pointer");
+  STEGO_CHECK_ARG(M > 0 && N > 0 && K > 0, "stego_gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
+  STEGO_CHECK_ARG(K % GEMM_BK == 0, "stego_gemm_bf16: K=%d must be a multiple of 64 (zero-pad the operands)", K);
+  STEGO_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "stego_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  STEGO_CHECK_ARG(act >= 0 && act <= 2, "stego_gemm_bf16: act=%d", act);
+  STEGO_CHECK_ARG(!(atomic_out && out_bf16), "stego_gemm_bf16: atomic output must be fp32");
+  STEGO_CHECK_ARG(splits >= 1, "stego_gemm_bf16: splits=%d", splits);
+  STEGO_CHECK_ARG(splits == 1 || atomic_out, "stego_gemm_bf16: split-K requires atomic_out");
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  const int num_kb = K / GEMM_BK;
+  if (splits > num_kb) splits = num_kb;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16;
+  p.bias = bias; p.act = act;
+  p.residual = residual; p.ldr = ldr;
+  p.row_div = row_div; p.atomic = atomic_out;
+  const size_t esz = out_bf16 ? 2 : 4;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((size_t(ldo) * esz) % 16 == 0) &&
+             (residual == nullptr || (((reinterpret_cast<uintptr_t>(residual) & 15u) == 0) && (size_t(ldr) * 4) % 16 == 0));
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  {
+    // K-major: tensor is [M][K] (inner = K). MN-major: tensor is [K][M] (inner = M).
+    uint64_t dims[2] = {a_mn_major ? (uint64_t)M : (uint64_t)K, a_mn_major ? (uint64_t)K : (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {64, a_mn_major ? 64u : (uint32_t)GEMM_BM};
+    if ((rc = make_tmap_bf16(&tmA, A, 2, dims, str, box)) != STEGO_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {64, b_mn_major ? 64u : 128u};
+    if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
+  }
+  if (!a_mn_major && !b_mn_major) return launch_gemm<128, 6, false, false>(tmA, tmB, p, stream);
+  if (!a_mn_major && b_mn_major) return launch_gemm<128, 6, false, true>(tmA, tmB, p, stream);
+  if (a_mn_major && b_mn_major) return launch_gemm<128, 6, true, true>(tmA, tmB, p, stream);
+  return launch_gemm<128, 6, true, false>(tmA, tmB, p, stream);
+}
