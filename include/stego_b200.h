@@ -51,6 +51,65 @@ STEGO_API int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void
                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Frozen DINO ViT forward pieces (reference: src/dino/vision_transformer.py)
+ * ---------------------------------------------------------------------------------------------- */
+/* PatchEmbed conv (:127-131) as im2col: img [B][3][H][W] fp32 -> rows [B*(H/p)*(W/p)][3*p*p] bf16,
+ * column order = flattening of the conv weight [E][3][p][p]. */
+STEGO_API int stego_vit_patchify(const float* img, void* out_bf16, int B, int H, int W, int patch, void* stream);
+/* prepare_tokens (:203-207): x[b][0][:] = cls_token + pos_embed[0] (fp32 residual stream [B][ntok][E]). */
+STEGO_API int stego_vit_cls_rows(float* x, const float* cls_token, const float* pos_embed, int B, int ntok, int E,
+                                 void* stream);
+/* nn.LayerNorm (:107,111,234): fp32 rows [rows][E] -> bf16. drop_cls_ntok > 0: rows are tokens of images with
+ * that many tokens each; the cls token (token 0) is dropped and the output packed [B][ntok-1][E]
+ * (src/modules.py:97). E in {128, 384, 768}. */
+STEGO_API int stego_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows,
+                                   int E, float eps, int drop_cls_ntok, void* stream);
+/* Attention.forward (:78-90) without the projections: softmax(q k^T / sqrt(64)) v, fused (flash-style) on
+ * tcgen05; qkv [B][N][3E] bf16 packed q|k|v with heads contiguous inside each third, out [B][N][E] bf16. */
+STEGO_API int stego_attention_fwd(const void* qkv, void* out, int B, int N, int E, int heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Correspondence loss (reference: src/modules.py:275-295, 325-398)
+ *
+ * "slot" = one distinct sampled operand: 0 = (src, coords1), 1 = (src_pos, coords2),
+ * 2+i = (src[perm_i], coords2).  "call" = one ContrastiveCorrelationLoss.helper invocation; its A
+ * operand is always slot 0 and its B operand is slot_of_call[call].
+ * Operand tiles: bf16 [2 planes (hi, lo)][nslots][B][128][Cpad]; rows >= feature_samples^2 are zero.
+ * ---------------------------------------------------------------------------------------------- */
+/* sample (:287-288) + norm (:275-276): bilinear border/align_corners=True gather at the coords, optional
+ * per-(image,channel) scale (the Dropout2d noise of modules.py:116), L2 normalise (eps 1e-10), write
+ * the hi/lo split tiles.  src strides are in elements; coords are [B][fs][fs][2] fp32;
+ * perms [nslots-2][B] int64 (already super_perm'ed, :291-295). */
+STEGO_API int stego_sample_norm_fwd(const void* src, const void* src_pos, int src_is_bf16, long long stride_b,
+                                    long long stride_c, long long stride_y, long long stride_x,
+                                    const float* chan_scale, const float* chan_scale_pos, const float* coords1,
+                                    const float* coords2, const long long* perms, void* tiles, int B, int C,
+                                    int Cpad, int H, int W, int feature_samples, int nslots, void* stream);
+/* helper (:325-347) for all calls at once: fd and cd einsums on tcgen05 (bf16 hi/lo split, fp32 accumulate),
+ * pointwise centring, clamp, shift, product and reduction.  slot_of_call / shifts are HOST arrays.
+ * partials: scratch [ncalls][B][8]; stats: out [ncalls][4] = {mean loss, mean cd, old_mean, mean of centred fd}.
+ * Optional (may be null): cd_out / fdc_out / loss_out [ncalls][B][S][S] (loss_out needs the other two). */
+STEGO_API int stego_corr_loss_fwd(const void* feat_tiles, const void* code_tiles, int B, int feature_samples, int E,
+                                  int D, int nslots, int ncalls, const int* slot_of_call_host,
+                                  const float* shifts_host, int pointwise, int zero_clamp, int stabilize,
+                                  float* partials, float* stats, float* cd_out, float* fdc_out, float* loss_out,
+                                  void* stream);
+/* Backward of the above wrt the normalised code tiles.  gscale [ncalls] = upstream gradient of each call's mean
+ * loss; gelem / gcd (optional) = upstream gradients of the unreduced loss / cd elements [ncalls][B][S][S].
+ * dtiles: fp32 [nslots][B][128][72], must be zero on entry, receives d(loss)/d(normalised sampled code). */
+STEGO_API int stego_corr_loss_bwd(const void* feat_tiles, const void* code_tiles, int B, int feature_samples, int E,
+                                  int D, int nslots, int ncalls, const int* slot_of_call_host,
+                                  const float* shifts_host, int pointwise, int zero_clamp, int stabilize,
+                                  const float* stats, const float* gscale, const float* gelem, const float* gcd,
+                                  float* dtiles, void* stream);
+/* Backward of norm + sample for the code tensors: scatter-adds into dcode / dcode_pos (same strides as code). */
+STEGO_API int stego_sample_norm_bwd(const float* code, const float* code_pos, long long stride_b, long long stride_c,
+                                    long long stride_y, long long stride_x, const float* coords1,
+                                    const float* coords2, const long long* perms, const float* dtiles, float* dcode,
+                                    float* dcode_pos, int B, int C, int H, int W, int feature_samples, int nslots,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

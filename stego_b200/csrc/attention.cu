@@ -1,0 +1,322 @@
+// Fused multi-head self-attention forward for the frozen DINO ViT (sm_100a, tcgen05 + TMA + TMEM).
+//
+// Reference: src/dino/vision_transformer.py:78-90 (Attention.forward):
+//     attn = softmax(q k^T * head_dim^-0.5);  x = attn v
+// The reference materialises the [B, heads, N, N] fp32 score tensor three times per layer; here it
+// never leaves the SM: S = Q K^T accumulates in TMEM, softmax runs out of TMEM in registers,
+// P (bf16) goes through swizzled shared memory straight back into the tensor core for P V.
+//
+// One CTA per (128-query tile, head, image), head_dim = 64, 320 threads:
+//   warp 0      TMA producer: Q tile once, then a 3-stage ring of (K,V) tiles
+//   warp 1      MMA issuer  : S_j = Q K_j^T (128x128x64), O_j = P_j V_j (128x64x128)
+//   warps 2..5  softmax warpgroup 0  (KV tiles 0,2,4,..)   } each thread owns one query row, keeps its own
+//   warps 6..9  softmax warpgroup 1  (KV tiles 1,3,5,..)   } running max / sum / fp32 output accumulator
+// The two warpgroups work on alternate KV tiles (S, P, O are double buffered) and are merged once at the
+// end (split-KV combine), so there is no cross-warpgroup dependency inside the loop.
+// Input is the packed qkv GEMM output [B, N, 3E] bf16 (q | k | v, head-major inside each), read through
+// ONE 3-D tensor map; rows past N (ragged last tile: N = hw + 1 is never a multiple of 128) are
+// zero-filled by TMA and masked to -inf in the softmax.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace stego {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+constexpr int ATT_D = 64;
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_THREADS = 320;
+
+constexpr uint32_t ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128][64] bf16 tile
+constexpr uint32_t ATT_SMEM_Q = 0;
+constexpr uint32_t ATT_SMEM_KV = ATT_TILE_BYTES;                                   // stages x (K,V)
+constexpr uint32_t ATT_SMEM_P = ATT_SMEM_KV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 32 KB
+constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_P + 2 * 2 * ATT_TILE_BYTES;              // m,l of WG1: 2 x 128 floats
+constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_ML + 1024;
+constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256 + 1024;  // + alignment slack
+
+struct AttnParams {
+  bf16* out;   // [B*N][E] bf16 (heads concatenated, like .transpose(1,2).reshape(B,N,C))
+  int N;       // tokens per image
+  int E;       // embed dim = heads * 64
+  float scale_log2e;  // head_dim^-0.5 * log2(e)
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
+  uint64_t* q_full = bars;                        // [1]
+  uint64_t* kv_full = bars + 1;                   // [STAGES]
+  uint64_t* kv_empty = kv_full + ATT_STAGES;      // [STAGES]
+  uint64_t* s_full = kv_empty + ATT_STAGES;       // [2]
+  uint64_t* s_empty = s_full + 2;                 // [2]
+  uint64_t* p_full = s_empty + 2;                 // [2]
+  uint64_t* o_full = p_full + 2;                  // [2]
+  uint64_t* o_empty = o_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 4);
+      mbar_init(&p_full[b], 4);
+      mbar_init(&o_full[b], 1);
+      mbar_init(&o_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S[b] at + b*128
+  const uint32_t TM_O = tmem_base + 256;   // O[b] at + b*64
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(smem + ATT_SMEM_Q, &tmQKV, q_full, head * ATT_D, q0, img);
+      uint32_t stage = 0, phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES;
+        uint8_t* sv = sk + ATT_TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_3d(sk, &tmQKV, &kv_full[stage], p.E + head * ATT_D, j * ATT_BKV, img);
+        tma_load_3d(sv, &tmQKV, &kv_full[stage], 2 * p.E + head * ATT_D, j * ATT_BKV, img);
+        if (++stage == ATT_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major: d contiguous)
+      const uint32_t sq = smem_u32(smem + ATT_SMEM_Q);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      auto issue_pv = [&](int i) {
+        const int b = i & 1;
+        const uint32_t it = static_cast<uint32_t>(i >> 1);
+        const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
+        mbar_wait(&p_full[b], it & 1u);
+        mbar_wait(&o_empty[b], (it & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + ATT_SMEM_P + b * 2 * ATT_TILE_BYTES);
+        const uint32_t sv = smem_u32(smem + ATT_SMEM_KV + stage_i * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 8192, 1024);
+          umma_bf16(TM_O + b * 64, da, db, IDESC_O, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[b]);
+        umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
+      };
+      uint32_t stage = 0, phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const uint32_t it = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&kv_full[stage], phase);
+        mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
+          umma_bf16(TM_S + b * 128, da, db, IDESC_S, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[b]);
+        if (j > 0) issue_pv(j - 1);
+        if (++stage == ATT_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      issue_pv(nkv - 1);
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int wg = (warp - 2) >> 2;  // 0 or 1
+    const int quarter = warp & 3;    // TMEM lane quarter accessible to this warp
+    const int r = quarter * 32 + lane;  // query row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint8_t* sp = smem + ATT_SMEM_P + wg * 2 * ATT_TILE_BYTES;
+    float acc[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c = p.scale_log2e;
+
+    uint32_t it = 0;
+    for (int j = wg; j < nkv; j += 2, ++it) {
+      const int valid = p.N - j * ATT_BKV;  // number of real keys in this tile (>= 1)
+      mbar_wait(&s_full[wg], it & 1u);
+      tc_fence_after();
+      const uint32_t ts = TM_S + wg * 128 + lane_off;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(ts + ch * 32, v);
+        tmem_ld_wait();
+        if (valid >= ch * 32 + 32) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (ch * 32 + t < valid) mx = fmaxf(mx, __uint_as_float(v[t]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float mc = m_new * c;
+      // pass 2: p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem
+      float rs = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(ts + ch * 32, v);
+        tmem_ld_wait();
+        float e[32];
+        if (valid >= ch * 32 + 32) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) e[t] = exp2f(fmaf(__uint_as_float(v[t]), c, -mc));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) e[t] = (ch * 32 + t < valid) ? exp2f(fmaf(__uint_as_float(v[t]), c, -mc)) : 0.f;
+        }
+        uint8_t* blk = sp + (ch >> 1) * ATT_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          // round to bf16 first and sum the ROUNDED values so that l matches what the MMA consumes
+          uint4 w;
+          w.x = pack_bf16x2(e[8 * g + 0], e[8 * g + 1]);
+          w.y = pack_bf16x2(e[8 * g + 2], e[8 * g + 3]);
+          w.z = pack_bf16x2(e[8 * g + 4], e[8 * g + 5]);
+          w.w = pack_bf16x2(e[8 * g + 6], e[8 * g + 7]);
+          *reinterpret_cast<uint4*>(blk + sw128_offset(r, (ch & 1) * 4 + g)) = w;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) rs += e[8 * g + t];
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[wg]);
+        mbar_arrive(&p_full[wg]);
+      }
+      const float alpha = exp2f((m_run - m_new) * c);  // m_run = -inf on the first tile -> 0
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      // O_j = P_j V_j lands in TMEM; fold it into the running fp32 accumulator
+      mbar_wait(&o_full[wg], it & 1u);
+      tc_fence_after();
+      const uint32_t to = TM_O + wg * 64 + lane_off;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(to + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) acc[h * 32 + t] = fmaf(acc[h * 32 + t], alpha, __uint_as_float(v[t]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[wg]);
+    }
+
+    // ---- combine the two warpgroups (split-KV merge) and write the output ----
+    float* xch = reinterpret_cast<float*>(smem + ATT_SMEM_P + 2 * ATT_TILE_BYTES);  // P[1] buffer: [64][128] floats
+    float* ml = reinterpret_cast<float*>(smem + ATT_SMEM_ML);                       // [2][128]
+    if (wg == 1) {
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) xch[d * 128 + r] = acc[d];
+      ml[r] = m_run;
+      ml[128 + r] = l_run;
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 softmax warps only
+    if (wg == 0) {
+      const float m1 = ml[r], l1 = ml[128 + r];
+      const float m = fmaxf(m_run, m1);
+      const float a0 = exp2f((m_run - m) * c);
+      const float a1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - m) * c);
+      const float inv = 1.0f / (l_run * a0 + l1 * a1);
+      const int q = q0 + r;
+      if (q < p.N) {
+        bf16* o = p.out + (static_cast<size_t>(img) * p.N + q) * p.E + head * ATT_D;
+#pragma unroll
+        for (int g = 0; g < ATT_D / 8; ++g) {
+          float y[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) y[t] = (acc[8 * g + t] * a0 + xch[(8 * g + t) * 128 + r] * a1) * inv;
+          uint4 w;
+          w.x = pack_bf16x2(y[0], y[1]);
+          w.y = pack_bf16x2(y[2], y[3]);
+          w.z = pack_bf16x2(y[4], y[5]);
+          w.w = pack_bf16x2(y[6], y[7]);
+          reinterpret_cast<uint4*>(o)[g] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace stego
+
+using namespace stego;
+
+// qkv: [B][N][3E] bf16 packed (q|k|v), out: [B][N][E] bf16.
+extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int E, int heads, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(qkv && out, "stego_attention_fwd: null pointer");
+  STEGO_CHECK_ARG(B > 0 && N > 0 && heads > 0, "stego_attention_fwd: bad sizes");
+  STEGO_CHECK_ARG(E == heads * ATT_D, "stego_attention_fwd: head_dim must be 64 (E=%d heads=%d)", E, heads);
+  STEGO_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "stego_attention_fwd: out not 16-byte aligned");
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)3 * E, (uint64_t)N, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)3 * E * 2, (uint64_t)N * 3 * E * 2};
+  uint32_t box[3] = {64, 128, 1};
+  int rc = make_tmap_bf16(&tm, qkv, 3, dims, str, box);
+  if (rc != STEGO_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ATT_SMEM_TOTAL);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attention)");
+    configured = true;
+  }
+  AttnParams p;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.N = N;
+  p.E = E;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, p);
+  STEGO_CHECK_LAUNCH("attention_fwd_kernel");
+  return STEGO_OK;
+}

@@ -1,0 +1,150 @@
+// Bandwidth-bound pieces of the frozen DINO ViT forward (reference: src/dino/vision_transformer.py):
+//   patchify      : NCHW fp32 image -> im2col rows [B*hw][3*P*P] bf16  (PatchEmbed conv, :127-131, as a GEMM operand)
+//   cls rows      : x[b,0,:] = cls_token + pos_embed[0]                 (prepare_tokens, :203-207)
+//   layernorm     : fp32 residual stream -> bf16 GEMM operand            (Block norm1/norm2 :107,111; final norm :234)
+// The residual stream is kept in fp32 (the reference computes in fp32); GEMM operands are bf16.
+// All kernels are HBM-bound: 16-byte vector accesses, one warp per row, no shared memory needed.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace stego {
+
+// ---------------------------------------------------------------------------------------------
+// patchify: one thread per (patch, channel, ky): reads P contiguous pixels, writes P bf16.
+// column order c*P*P + ky*P + kx == flattening of the conv weight [E][3][P][P].
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W) {
+  const int fh = H / P, fw = W / P;
+  const long long total = 1ll * B * fh * fw * 3 * P;
+  const long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ky = idx % P;
+  const int c = (idx / P) % 3;
+  const long long patch = idx / (3 * P);
+  const int px = patch % fw;
+  const int py = (patch / fw) % fh;
+  const int b = patch / (1ll * fw * fh);
+  const float* src = img + ((1ll * b * 3 + c) * H + (py * P + ky)) * W + px * P;
+  bf16* dst = out + patch * (3 * P * P) + c * P * P + ky * P;
+  static_assert(P == 8 || P == 16, "patch size");
+#pragma unroll
+  for (int v = 0; v < P / 8; ++v) {
+    const float4 a = *reinterpret_cast<const float4*>(src + v * 8);
+    const float4 b4 = *reinterpret_cast<const float4*>(src + v * 8 + 4);
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y);
+    w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(b4.x, b4.y);
+    w.w = pack_bf16x2(b4.z, b4.w);
+    *reinterpret_cast<uint4*>(dst + v * 8) = w;
+  }
+}
+
+__global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int B, int ntok, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, e = i % E;
+  x[(1ll * b * ntok) * E + e] = cls[e] + pos[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (E = 128*V4 floats), two-pass statistics.
+// drop_cls > 0: rows are tokens of images with `drop_cls` tokens each; token 0 (cls) is skipped and
+// the output is packed tokens-major [B][ntok-1][E] (modules.py:97 drops the cls token).
+// ---------------------------------------------------------------------------------------------
+template <int V4>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 bf16* __restrict__ out, int rows, float eps, int drop_cls) {
+  constexpr int E = V4 * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  long long orow = row;
+  if (drop_cls > 0) {
+    const int t = row % drop_cls;
+    if (t == 0) return;
+    orow = 1ll * (row / drop_cls) * (drop_cls - 1) + (t - 1);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + 1ll * row * E);
+  float4 v[V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / E);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* o = reinterpret_cast<uint2*>(out + orow * E);
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i);
+    const float4 bb = __ldg(b4 + lane + 32 * i);
+    uint2 w;
+    w.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+    w.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    o[lane + 32 * i] = w;
+  }
+}
+
+}  // namespace stego
+
+using namespace stego;
+
+extern "C" int stego_vit_patchify(const float* img, void* out_bf16, int B, int H, int W, int patch, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(img && out_bf16, "stego_vit_patchify: null pointer");
+  STEGO_CHECK_ARG(patch == 8 || patch == 16, "stego_vit_patchify: patch size %d unsupported (8 or 16)", patch);
+  STEGO_CHECK_ARG(B > 0 && H % patch == 0 && W % patch == 0 && W % 4 == 0, "stego_vit_patchify: bad image %dx%dx%d", B, H, W);
+  STEGO_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15u) == 0, "stego_vit_patchify: image not 16-byte aligned");
+  const long long total = 1ll * B * (H / patch) * (W / patch) * 3 * patch;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads);
+  if (patch == 8)
+    patchify_kernel<8><<<blocks, threads, 0, stream>>>(img, reinterpret_cast<bf16*>(out_bf16), B, H, W);
+  else
+    patchify_kernel<16><<<blocks, threads, 0, stream>>>(img, reinterpret_cast<bf16*>(out_bf16), B, H, W);
+  STEGO_CHECK_LAUNCH("patchify_kernel");
+  return STEGO_OK;
+}
+
+extern "C" int stego_vit_cls_rows(float* x, const float* cls_token, const float* pos_embed, int B, int ntok, int E,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(x && cls_token && pos_embed && B > 0 && ntok > 0 && E > 0, "stego_vit_cls_rows: bad args");
+  cls_rows_kernel<<<(B * E + 255) / 256, 256, 0, stream>>>(x, cls_token, pos_embed, B, ntok, E);
+  STEGO_CHECK_LAUNCH("cls_rows_kernel");
+  return STEGO_OK;
+}
+
+extern "C" int stego_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows,
+                                    int E, float eps, int drop_cls_ntok, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(x && gamma && beta && out_bf16 && rows > 0, "stego_layernorm_bf16: bad args");
+  STEGO_CHECK_ARG(drop_cls_ntok == 0 || rows % drop_cls_ntok == 0, "stego_layernorm_bf16: rows %% ntok != 0");
+  const int warps = 8;
+  const int blocks = (rows + warps - 1) / warps;
+  bf16* o = reinterpret_cast<bf16*>(out_bf16);
+  switch (E) {
+    case 384: layernorm_kernel<3><<<blocks, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, eps, drop_cls_ntok); break;
+    case 768: layernorm_kernel<6><<<blocks, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, eps, drop_cls_ntok); break;
+    case 128: layernorm_kernel<1><<<blocks, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, eps, drop_cls_ntok); break;
+    case 192: /* vit_tiny: 1.5 x 128 — not a multiple */
+    default:
+      set_error("stego_layernorm_bf16: embed dim %d unsupported (128, 384, 768)", E);
+      return STEGO_ERR_UNSUPPORTED;
+  }
+  STEGO_CHECK_LAUNCH("layernorm_kernel");
+  return STEGO_OK;
+}

@@ -36,3 +36,40 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         _lib.stream())
     _lib.check(rc, "stego_gemm_bf16")
     return out
+
+
+def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
+    """PatchEmbed im2col rows [B*hw, 3*p*p] bf16 (stego_vit_patchify)."""
+    _lib.require_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
+    B, _, H, W = img.shape
+    out = torch.empty(B * (H // patch) * (W // patch), 3 * patch * patch, dtype=torch.bfloat16, device=img.device)
+    _lib.check(_lib.load().stego_vit_patchify(_lib.ptr(img), _lib.ptr(out), B, H, W, patch, _lib.stream()),
+               "stego_vit_patchify")
+    return out
+
+
+def cls_rows(x: torch.Tensor, cls_token: torch.Tensor, pos_embed: torch.Tensor, B: int, ntok: int) -> None:
+    E = x.shape[-1]
+    _lib.check(_lib.load().stego_vit_cls_rows(_lib.ptr(x), _lib.ptr(cls_token), _lib.ptr(pos_embed), B, ntok, E,
+                                              _lib.stream()), "stego_vit_cls_rows")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-6,
+              drop_cls_ntok: int = 0) -> torch.Tensor:
+    """fp32 [rows,E] -> bf16 LayerNorm (stego_layernorm_bf16)."""
+    _lib.require_cuda(x, gamma, beta, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    rows, E = x.shape
+    _lib.check(_lib.load().stego_layernorm_bf16(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out), rows, E,
+                                                eps, drop_cls_ntok, _lib.stream()), "stego_layernorm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, N: int, E: int, heads: int) -> torch.Tensor:
+    """Fused softmax(q k^T / 8) v on tcgen05 (stego_attention_fwd). qkv [B*N, 3E] bf16, out [B*N, E] bf16."""
+    _lib.require_cuda(qkv, out)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    _lib.check(_lib.load().stego_attention_fwd(_lib.ptr(qkv), _lib.ptr(out), B, N, E, heads, _lib.stream()),
+               "stego_attention_fwd")
+    return out
