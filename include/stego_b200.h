@@ -39,7 +39,7 @@ STEGO_API const char* stego_last_error(void);
  *   src/modules.py:73-81 (cluster1 / cluster2 heads) and their autograd backward (dgrad, wgrad).
  *   a_mn_major = 0: A is [M][lda] (K contiguous);   1: A is stored transposed, [K][lda] (M contiguous)
  *   b_mn_major = 0: B is [N][ldb] (K contiguous);   1: B is [K][ldb] (N contiguous)
- *   K must be a multiple of 64 (zero-pad operands); lda/ldb multiples of 8.
+ *   lda/ldb multiples of 8 elements (16-byte rows for TMA); a K tail (K % 64 != 0) is zero-filled by TMA.
  *   act: 0 none, 1 GELU(erf) (nn.GELU default), 2 ReLU.
  *   residual: fp32 [M][ldr] added after the activation (may alias out for an in-place update).
  *   row_div > 0 (patch-embed mode): output row r goes to r + r/row_div + 1 (skips the cls slot of
@@ -109,6 +109,54 @@ STEGO_API int stego_sample_norm_bwd(const float* code, const float* code_pos, lo
                                     const float* coords2, const long long* perms, const float* dtiles, float* dcode,
                                     float* dcode_pos, int B, int C, int H, int W, int feature_samples, int nslots,
                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segmentation head glue (reference: src/modules.py:73-81, 108-118) and optimiser
+ * ---------------------------------------------------------------------------------------------- */
+/* Apply the three Dropout2d noises of DinoFeaturizer.forward (:109,:111,:116) in one pass:
+ * out_i[b][p][c] = feat[b][p][c] * mask_i[b][c]; feat/out tokens-major bf16 [B*hw][E]; mask fp32 [B][E].
+ * Any (mask_i, out_i) pair may be null. */
+STEGO_API int stego_head_dropout3(const void* feat_bf16, const float* mask1, const float* mask2, const float* mask3,
+                                  void* out1, void* out2, void* out3, int B, int hw, int E, void* stream);
+/* fp32 [rows][ld_in] (first C columns) -> bf16 [rows][ld_out] zero-padded: packs d(code) as a GEMM operand. */
+STEGO_API int stego_cast_pad_bf16(const float* in, int ld_in, int C, void* out_bf16, int ld_out, long long rows,
+                                  void* stream);
+/* ReLU backward between the two cluster2 convs: out = bf16(dh * (h > 0)), n elements (multiple of 4). */
+STEGO_API int stego_relu_bwd_bf16(const float* dh, const void* h_bf16, void* out_bf16, long long n, void* stream);
+/* Bias gradients: out[C] += column sums of in [rows][ld] (fp32 or bf16). */
+STEGO_API int stego_colsum(const void* in, int in_is_bf16, int ld, int C, long long rows, float* out, void* stream);
+/* torch.optim.Adam step (src/train_segmentation.py:379-381; amsgrad off, weight_decay 0) on a flat fp32 buffer;
+ * `step` is 1-based; grad is multiplied by grad_scale first (1/world_size after a sum-allreduce). */
+STEGO_API int stego_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                              float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Probes
+ * ---------------------------------------------------------------------------------------------- */
+/* ClusterLookup.forward (src/modules.py:146-161). x has element strides (batch, channel, pixel) with
+ * pixel = y*W + x; clusters [n][C].  use_alpha = 0 is `alpha is None` (one-hot argmax).
+ * loss_out[0] = -(probs * inner_products).sum(1).mean().  Optional outputs (may be null): assign [B][npix]
+ * int64 argmax, probs [B][n][npix], log_probs [B][n][npix] (needs alpha).  scratch: >= 8*SMs floats. */
+STEGO_API int stego_cluster_lookup_fwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
+                                       const float* clusters, int B, int C, int n_classes, long long npix,
+                                       int use_alpha, float alpha, long long* assign, float* probs, float* log_probs,
+                                       float* loss_out, float* scratch, void* stream);
+/* Gradient of the ClusterLookup loss wrt the centroids: dclusters += grad_loss_dev[0] * dloss/dclusters
+ * (the upstream scalar is a DEVICE pointer so autograd never synchronises). dnc_scratch [n][C] zero on entry. */
+STEGO_API int stego_cluster_lookup_bwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
+                                       const float* clusters, int B, int C, int n_classes, long long npix,
+                                       int use_alpha, float alpha, const float* grad_loss_dev,
+                                       float* dnc_scratch, float* dclusters, void* stream);
+/* Linear probe step (src/train_segmentation.py:213-218): 1x1 conv on tokens-major code [B*h*w][ld_code],
+ * bilinear upsample to [H][W] (align_corners=False), CrossEntropyLoss over pixels with 0 <= label < n.
+ * loss_out[0] = mean CE, loss_out[1] = valid pixel count.  If dlogits_scratch is non-null (zeroed by the
+ * caller) the backward also runs: dW [n][C] and db [n] += grad_loss * gradient.
+ * logits_scratch / dlogits_scratch: [B*h*w][32] floats; partials_scratch: >= 16*SMs floats. */
+STEGO_API int stego_linear_probe_ce(const float* code, long long ld_code, int C, const float* W, const float* bias,
+                                    int n_classes, const long long* label, int B, int h, int w, int H, int Wimg,
+                                    float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
+                                    float* loss_out, float grad_loss, float* dW, float* db, void* stream);
 
 #ifdef __cplusplus
 }

@@ -319,14 +319,24 @@ def draw_dropout2d_mask(batch: int, channels: int, p: float = 0.1, device="cpu")
     return torch.empty(batch, channels, 1, 1, device=device).bernoulli_(1 - p).div_(1 - p)
 
 
-def head_forward(image_feat: Tensor, hp: Dict[str, Tensor], masks: Optional[Sequence[Tensor]]):
+def _bf16_round(t: Tensor) -> Tensor:
+    """Straight-through bf16 rounding (identity gradient): emulates where a bf16 autocast run of the
+    reference would round GEMM operands, so the CUDA path can be compared at the 1e-3 bar."""
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def head_forward(image_feat: Tensor, hp: Dict[str, Tensor], masks: Optional[Sequence[Tensor]],
+                 round_bf16: bool = False):
     """modules.py:108-118 with proj_type='nonlinear': code = cluster1(drop(f)) + cluster2(drop(f));
     returns (drop(f) if dropout else f, code).  `masks` = the three Dropout2d noise tensors in call
-    order (cluster1 input, cluster2 input, returned feats), or None for eval / dropout off."""
+    order (cluster1 input, cluster2 input, returned feats), or None for eval / dropout off.
+    round_bf16=True rounds every GEMM operand (masked inputs, weights, hidden activation) to bf16 with
+    fp32 accumulation — the reference under bf16 autocast."""
     m1, m2, m3 = masks if masks is not None else (1.0, 1.0, 1.0)
-    code = F.conv2d(image_feat * m1, hp["cluster1.0.weight"], hp["cluster1.0.bias"])
-    h = torch.relu(F.conv2d(image_feat * m2, hp["cluster2.0.weight"], hp["cluster2.0.bias"]))
-    code = code + F.conv2d(h, hp["cluster2.2.weight"], hp["cluster2.2.bias"])
+    r = _bf16_round if round_bf16 else (lambda t: t)
+    code = F.conv2d(r(image_feat * m1), r(hp["cluster1.0.weight"]), hp["cluster1.0.bias"])
+    h = torch.relu(F.conv2d(r(image_feat * m2), r(hp["cluster2.0.weight"]), hp["cluster2.0.bias"]))
+    code = code + F.conv2d(r(h), r(hp["cluster2.2.weight"]), hp["cluster2.2.bias"])
     return image_feat * m3, code
 
 
@@ -355,11 +365,12 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, 
 
 
 def training_losses(image_feat: Tensor, image_feat_pos: Tensor, hp: Dict[str, Tensor], probes: Dict[str, Tensor],
-                    label: Tensor, masks, masks_pos, coords1, coords2, perms, cfg: LossCfg, n_classes: int):
+                    label: Tensor, masks, masks_pos, coords1, coords2, perms, cfg: LossCfg, n_classes: int,
+                    round_bf16: bool = False):
     """Loss assembly of training_step (train_segmentation.py:130-225) from frozen-backbone features.
     Returns dict of scalar losses; `total` is what manual_backward receives."""
-    feats, code = head_forward(image_feat, hp, masks)
-    feats_pos, code_pos = head_forward(image_feat_pos, hp, masks_pos)
+    feats, code = head_forward(image_feat, hp, masks, round_bf16)
+    feats_pos, code_pos = head_forward(image_feat_pos, hp, masks_pos, round_bf16)
     out6 = correlation_loss(feats, feats_pos, code, code_pos, coords1, coords2, perms, cfg)
     corr = weighted_correspondence_loss(out6, cfg)
     detached = code.detach().clone()

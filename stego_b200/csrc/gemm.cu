@@ -63,7 +63,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_kb = p.K / GEMM_BK;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;  // K tail: TMA zero-fills out-of-bounds
   const int total_tiles = tiles_m * tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
@@ -284,7 +284,6 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(A && B && out, "stego_gemm_bf16: null pointer");
   STEGO_CHECK_ARG(M > 0 && N > 0 && K > 0, "stego_gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
-  STEGO_CHECK_ARG(K % GEMM_BK == 0, "stego_gemm_bf16: K=%d must be a multiple of 64 (zero-pad the operands)", K);
   STEGO_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "stego_gemm_bf16: lda/ldb must be multiples of 8 elements");
   STEGO_CHECK_ARG(act >= 0 && act <= 2, "stego_gemm_bf16: act=%d", act);
   STEGO_CHECK_ARG(!(atomic_out && out_bf16), "stego_gemm_bf16: atomic output must be fp32");
@@ -293,7 +292,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  const int num_kb = K / GEMM_BK;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
   if (splits > num_kb) splits = num_kb;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;

@@ -1,0 +1,407 @@
+// Probe heads of the STEGO training / eval step (sm_100a; HBM-bound, fp32 arithmetic):
+//
+//   ClusterLookup            src/modules.py:134-161   cosine similarity to n_classes centroids,
+//                                                     argmax one-hot / softmax(alpha.) / log_softmax(alpha.), loss
+//   linear probe + CE        src/train_segmentation.py:210-219
+//                                                     1x1 conv -> bilinear upsample (align_corners=False) -> masked CE
+//
+// Both are evaluated per pixel in registers; nothing of size [B, n_classes, H, W] is materialised unless the
+// caller asks for the probabilities.  Dot products are sequential fp32 FMAs in channel order, so the
+// argmax is deterministic; centroids are normalised once per CTA into shared memory.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace stego {
+
+constexpr int PR_MAX_CLASSES = 64;
+constexpr int PR_MAX_DIM = 96;
+constexpr int PR_THREADS = 128;
+
+struct ClusterParams {
+  const float* x;            // features, element strides below
+  long long sb, sc, sp;      // batch / channel / pixel strides (pixel index = y*W + x must be affine: sp)
+  const float* clusters;     // [n][C]
+  int B, C, n;
+  long long npix;            // pixels per image (H*W)
+  int mode;                  // 0: alpha=None (argmax one-hot), 1: softmax(alpha * ip)
+  float alpha;
+  long long* assign;         // optional [B][npix] argmax
+  float* probs;              // optional [B][n][npix] (one-hot or softmax)
+  float* logp;               // optional [B][n][npix] log_softmax(alpha * ip)
+  float* loss_partials;      // [gridDim.x] sum over pixels of sum_k probs_k * ip_k
+  // backward
+  const float* grad_loss;    // device scalar: upstream gradient of the loss
+  float grad_scale;          // -1 / (B*npix)
+  float* dnc;                // [n][C] gradient wrt the NORMALISED centroids (atomically accumulated)
+};
+
+__device__ __forceinline__ void load_norm_clusters(const ClusterParams& p, float* snc) {
+  // normalise centroids (F.normalize, eps 1e-12) into smem: one warp per centroid round-robin
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < p.n; k += nw) {
+    float ss = 0.f;
+    for (int c = lane; c < p.C; c += 32) { const float v = p.clusters[k * p.C + c]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < p.C; c += 32) snc[k * p.C + c] = p.clusters[k * p.C + c] * inv;
+  }
+  __syncthreads();
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(PR_THREADS)
+cluster_lookup_kernel(ClusterParams p) {
+  extern __shared__ float sm[];
+  float* snc = sm;                         // [n][C]
+  float* sacc = sm + p.n * p.C;            // backward: [n][C] block accumulator
+  float* sred = sacc + (kBackward ? p.n * p.C : 0);  // [4]
+  load_norm_clusters(p, snc);
+  if (kBackward) p.grad_scale *= p.grad_loss[0];
+  if (kBackward) {
+    for (int i = threadIdx.x; i < p.n * p.C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  const long long total = 1ll * p.B * p.npix;
+  float loss_acc = 0.f;
+  for (long long pix = 1ll * blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += 1ll * gridDim.x * blockDim.x) {
+    const int b = static_cast<int>(pix / p.npix);
+    const long long q = pix % p.npix;
+    const float* xp = p.x + b * p.sb + q * p.sp;
+    float xv[PR_MAX_DIM];
+    float ss = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < p.C; ++c) { xv[c] = xp[c * p.sc]; ss += xv[c] * xv[c]; }
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    float ip[PR_MAX_CLASSES];
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < p.n; ++k) {
+      float d = 0.f;
+      const float* ck = snc + k * p.C;
+#pragma unroll 8
+      for (int c = 0; c < p.C; ++c) d = fmaf(xv[c] * inv, ck[c], d);
+      ip[k] = d;
+      if (d > best) { best = d; arg = k; }  // first maximum wins, like torch.argmax
+    }
+    if (p.mode == 0) {
+      loss_acc += best;
+      if (!kBackward) {
+        if (p.assign) p.assign[pix] = arg;
+        if (p.probs)
+          for (int k = 0; k < p.n; ++k) p.probs[(1ll * b * p.n + k) * p.npix + q] = (k == arg) ? 1.f : 0.f;
+      } else {
+        for (int c = 0; c < p.C; ++c) atomicAdd(&sacc[arg * p.C + c], p.grad_scale * xv[c] * inv);
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int k = 0; k < p.n; ++k) mx = fmaxf(mx, ip[k] * p.alpha);
+      float se = 0.f;
+      for (int k = 0; k < p.n; ++k) se += expf(ip[k] * p.alpha - mx);
+      const float lse = mx + logf(se);
+      float dotp = 0.f;
+      for (int k = 0; k < p.n; ++k) dotp += expf(ip[k] * p.alpha - lse) * ip[k];
+      loss_acc += dotp;
+      if (!kBackward) {
+        if (p.assign) p.assign[pix] = arg;
+        for (int k = 0; k < p.n; ++k) {
+          const float lp = ip[k] * p.alpha - lse;
+          if (p.probs) p.probs[(1ll * b * p.n + k) * p.npix + q] = expf(lp);
+          if (p.logp) p.logp[(1ll * b * p.n + k) * p.npix + q] = lp;
+        }
+      } else {
+        for (int k = 0; k < p.n; ++k) {
+          const float pk = expf(ip[k] * p.alpha - lse);
+          const float dip = p.grad_scale * (pk + p.alpha * pk * (ip[k] - dotp));
+          for (int c = 0; c < p.C; ++c) atomicAdd(&sacc[k * p.C + c], dip * xv[c] * inv);
+        }
+      }
+    }
+  }
+  if (!kBackward) {
+    loss_acc = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) t += sred[w];
+      p.loss_partials[blockIdx.x] = t;
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n * p.C; i += blockDim.x)
+      if (sacc[i] != 0.f) atomicAdd(p.dnc + i, sacc[i]);
+  }
+}
+
+// d clusters from d normalised clusters: row-wise normalize backward
+__global__ void cluster_norm_bwd_kernel(const float* __restrict__ clusters, const float* __restrict__ dnc,
+                                        float* __restrict__ dclusters, int n, int C) {
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x;
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = clusters[k * C + c]; ss += v * v; dot += v * dnc[k * C + c]; }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float nrm = sqrtf(ss);
+  for (int c = lane; c < C; c += 32) {
+    float g;
+    if (nrm > 1e-12f) g = (dnc[k * C + c] - clusters[k * C + c] * dot / ss) / nrm;
+    else g = dnc[k * C + c] / 1e-12f;
+    dclusters[k * C + c] += g;
+  }
+}
+
+// out[0] = scale * sum(partials[0..n))   (deterministic, single block)
+__global__ void sum_partials_kernel(const float* __restrict__ partials, int n, float scale, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += static_cast<double>(partials[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = static_cast<float>(sh[0] * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// linear probe: low-res logits, then per hi-res pixel: bilinear interpolation + masked CE fwd/bwd
+// ---------------------------------------------------------------------------------------------
+constexpr int LP_LD = 32;  // row stride of the low-res logit / grad buffers (n_classes <= 32)
+
+__global__ void __launch_bounds__(128)
+linear_logits_kernel(const float* __restrict__ code, long long ld_code, int C, const float* __restrict__ W,
+                     const float* __restrict__ bias, int n, float* __restrict__ logits, long long rows) {
+  extern __shared__ float sw[];  // [n][C] + [n]
+  for (int i = threadIdx.x; i < n * C; i += blockDim.x) sw[i] = W[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sw[n * C + i] = bias[i];
+  __syncthreads();
+  const long long r = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float xv[PR_MAX_DIM];
+  for (int c = 0; c < C; ++c) xv[c] = code[r * ld_code + c];
+  for (int k = 0; k < n; ++k) {
+    float d = sw[n * C + k];
+    for (int c = 0; c < C; ++c) d = fmaf(xv[c], sw[k * C + c], d);
+    logits[r * LP_LD + k] = d;
+  }
+}
+
+struct LinearCEParams {
+  const float* logits;   // [B*h*w][LP_LD]
+  const long long* label;  // [B][H][W]
+  int B, h, w, H, W, n;
+  float* dlogits;        // [B*h*w][LP_LD] unnormalised gradient (atomics), or null (loss only)
+  float* partials;       // [gridDim.x][2]: loss sum, valid count
+};
+
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  // ATen area_pixel_compute_source_index (align_corners=False, non-cubic): clamp negative to 0
+  float s = scale * (dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = static_cast<int>(s);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - i0;
+}
+
+__global__ void __launch_bounds__(256)
+linear_ce_kernel(LinearCEParams p) {
+  __shared__ float sred[2][8];
+  const long long total = 1ll * p.B * p.H * p.W;
+  const float sy = static_cast<float>(p.h) / p.H, sx = static_cast<float>(p.w) / p.W;
+  float lsum = 0.f, cnt = 0.f;
+  for (long long pix = 1ll * blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += 1ll * gridDim.x * blockDim.x) {
+    const long long lab = p.label[pix];
+    if (lab < 0 || lab >= p.n) continue;
+    const int X = static_cast<int>(pix % p.W);
+    const int Y = static_cast<int>((pix / p.W) % p.H);
+    const int b = static_cast<int>(pix / (1ll * p.W * p.H));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(Y, sy, p.h, y0, y1, ly);
+    src_index(X, sx, p.w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const long long base = 1ll * b * p.h * p.w;
+    const float* l00 = p.logits + (base + y0 * p.w + x0) * LP_LD;
+    const float* l01 = p.logits + (base + y0 * p.w + x1) * LP_LD;
+    const float* l10 = p.logits + (base + y1 * p.w + x0) * LP_LD;
+    const float* l11 = p.logits + (base + y1 * p.w + x1) * LP_LD;
+    float z[LP_LD];
+    float mx = -INFINITY;
+    for (int k = 0; k < p.n; ++k) {
+      z[k] = w00 * l00[k] + w01 * l01[k] + w10 * l10[k] + w11 * l11[k];
+      mx = fmaxf(mx, z[k]);
+    }
+    float se = 0.f;
+    for (int k = 0; k < p.n; ++k) se += expf(z[k] - mx);
+    const float lse = mx + logf(se);
+    lsum += lse - z[lab];
+    cnt += 1.f;
+    if (p.dlogits) {
+      float* d00 = p.dlogits + (base + y0 * p.w + x0) * LP_LD;
+      float* d01 = p.dlogits + (base + y0 * p.w + x1) * LP_LD;
+      float* d10 = p.dlogits + (base + y1 * p.w + x0) * LP_LD;
+      float* d11 = p.dlogits + (base + y1 * p.w + x1) * LP_LD;
+      for (int k = 0; k < p.n; ++k) {
+        const float g = expf(z[k] - lse) - ((k == lab) ? 1.f : 0.f);
+        atomicAdd(d00 + k, g * w00);
+        atomicAdd(d01 + k, g * w01);
+        atomicAdd(d10 + k, g * w10);
+        atomicAdd(d11 + k, g * w11);
+      }
+    }
+  }
+  lsum = warp_sum(lsum);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = lsum; sred[1][threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += sred[0][w]; c += sred[1][w]; }
+    p.partials[2 * blockIdx.x] = a;
+    p.partials[2 * blockIdx.x + 1] = c;
+  }
+}
+
+// out[0] = loss_sum / count ; out[1] = count
+__global__ void linear_ce_finish_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
+  __shared__ double sh[2][256];
+  double a = 0, c = 0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { a += partials[2 * i]; c += partials[2 * i + 1]; }
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = static_cast<float>(sh[0][0] / sh[1][0]); out[1] = static_cast<float>(sh[1][0]); }
+}
+
+// dW[k][c] += (gscale/count) * sum_r dlogits[r][k] code[r][c];  db[k] += (gscale/count) * sum_r dlogits[r][k]
+__global__ void __launch_bounds__(128)
+linear_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ code, long long ld_code, int C, int n,
+                    long long rows, int rows_per_block, const float* __restrict__ loss_out, float gscale,
+                    float* __restrict__ dW, float* __restrict__ db) {
+  const int k = blockIdx.x;
+  const long long r0 = 1ll * blockIdx.y * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  const int c = threadIdx.x;
+  const float s = gscale / loss_out[1];
+  float acc = 0.f, accb = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float g = dlogits[r * LP_LD + k];
+    if (c < C) acc = fmaf(g, code[r * ld_code + c], acc);
+    accb += g;
+  }
+  if (c < C) atomicAdd(dW + k * C + c, acc * s);
+  if (c == 0) atomicAdd(db + k, accb * s);
+}
+
+}  // namespace stego
+
+using namespace stego;
+
+static int fill_cluster(ClusterParams& p, const float* x, long long sb, long long sc, long long sp,
+                        const float* clusters, int B, int C, int n, long long npix, int use_alpha, float alpha) {
+  STEGO_CHECK_ARG(x && clusters && B > 0 && npix > 0, "cluster_lookup: bad args");
+  STEGO_CHECK_ARG(C > 0 && C <= PR_MAX_DIM, "cluster_lookup: dim %d unsupported (<= %d)", C, PR_MAX_DIM);
+  STEGO_CHECK_ARG(n > 0 && n <= PR_MAX_CLASSES, "cluster_lookup: n_classes %d unsupported (<= %d)", n, PR_MAX_CLASSES);
+  p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.clusters = clusters;
+  p.B = B; p.C = C; p.n = n; p.npix = npix; p.mode = use_alpha ? 1 : 0; p.alpha = alpha;
+  p.assign = nullptr; p.probs = nullptr; p.logp = nullptr; p.loss_partials = nullptr; p.grad_loss = nullptr;
+  p.grad_scale = 0.f; p.dnc = nullptr;
+  return STEGO_OK;
+}
+
+static int cluster_grid(long long total) {
+  long long g = (total + PR_THREADS - 1) / PR_THREADS;
+  const long long cap = 8ll * num_sms();
+  return (int)(g < cap ? g : cap);
+}
+
+// x: features with element strides (batch, channel, pixel); pixel index = y*W + x must be a single stride.
+// loss_out[0] = -(sum_k probs_k ip_k).mean(); scratch: at least 8*SMs floats.
+extern "C" int stego_cluster_lookup_fwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
+                                        const float* clusters, int B, int C, int n_classes, long long npix,
+                                        int use_alpha, float alpha, long long* assign, float* probs, float* log_probs,
+                                        float* loss_out, float* scratch, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ClusterParams p;
+  int rc = fill_cluster(p, x, stride_b, stride_c, stride_pix, clusters, B, C, n_classes, npix, use_alpha, alpha);
+  if (rc != STEGO_OK) return rc;
+  STEGO_CHECK_ARG(loss_out && scratch, "stego_cluster_lookup_fwd: null loss_out/scratch");
+  STEGO_CHECK_ARG(!log_probs || use_alpha, "stego_cluster_lookup_fwd: log_probs needs alpha");
+  p.assign = assign; p.probs = probs; p.logp = log_probs; p.loss_partials = scratch;
+  const long long total = 1ll * B * npix;
+  const int grid = cluster_grid(total);
+  const size_t smem = (size_t)(n_classes * C + 8) * sizeof(float);
+  cluster_lookup_kernel<false><<<grid, PR_THREADS, smem, stream>>>(p);
+  STEGO_CHECK_LAUNCH("cluster_lookup_kernel<fwd>");
+  sum_partials_kernel<<<1, 256, 0, stream>>>(scratch, grid, (float)(-1.0 / (double)total), loss_out);
+  STEGO_CHECK_LAUNCH("sum_partials_kernel");
+  return STEGO_OK;
+}
+
+// dclusters [n][C] += grad_loss_dev[0] * d(loss)/d(clusters) (upstream scalar read on the device: no host sync). dnc_scratch: [n][C] floats, zeroed by the caller.
+extern "C" int stego_cluster_lookup_bwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
+                                        const float* clusters, int B, int C, int n_classes, long long npix,
+                                        int use_alpha, float alpha, const float* grad_loss_dev,
+                                        float* dnc_scratch, float* dclusters, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ClusterParams p;
+  int rc = fill_cluster(p, x, stride_b, stride_c, stride_pix, clusters, B, C, n_classes, npix, use_alpha, alpha);
+  if (rc != STEGO_OK) return rc;
+  STEGO_CHECK_ARG(dnc_scratch && dclusters && grad_loss_dev, "stego_cluster_lookup_bwd: null pointer");
+  const long long total = 1ll * B * npix;
+  p.grad_scale = (float)(-1.0 / (double)total);
+  p.grad_loss = grad_loss_dev;
+  p.dnc = dnc_scratch;
+  const int grid = cluster_grid(total);
+  const size_t smem = (size_t)(2 * n_classes * C + 8) * sizeof(float);
+  cluster_lookup_kernel<true><<<grid, PR_THREADS, smem, stream>>>(p);
+  STEGO_CHECK_LAUNCH("cluster_lookup_kernel<bwd>");
+  cluster_norm_bwd_kernel<<<n_classes, 32, 0, stream>>>(clusters, dnc_scratch, dclusters, n_classes, C);
+  STEGO_CHECK_LAUNCH("cluster_norm_bwd_kernel");
+  return STEGO_OK;
+}
+
+// Linear probe + bilinear upsample + masked cross entropy, forward and (optionally) backward in one call.
+//   code [B*h*w][ld_code] fp32 tokens-major (detached), W [n][C], bias [n], label [B][H][W] int64
+//   loss_out[0] = CE mean over valid pixels, loss_out[1] = number of valid pixels
+//   logits_scratch / dlogits_scratch: [B*h*w][32] floats (dlogits zeroed by the caller; null = forward only)
+//   dW / db: accumulated (+=) with grad_loss * d(loss)/d(.)
+extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C, const float* W, const float* bias,
+                                     int n_classes, const long long* label, int B, int h, int w, int H, int Wimg,
+                                     float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
+                                     float* loss_out, float grad_loss, float* dW, float* db, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(code && W && bias && label && logits_scratch && partials_scratch && loss_out,
+                  "stego_linear_probe_ce: null pointer");
+  STEGO_CHECK_ARG(C > 0 && C <= PR_MAX_DIM && n_classes > 0 && n_classes <= LP_LD,
+                  "stego_linear_probe_ce: C=%d n=%d unsupported", C, n_classes);
+  STEGO_CHECK_ARG(!dlogits_scratch || (dW && db), "stego_linear_probe_ce: backward needs dW and db");
+  const long long rows = 1ll * B * h * w;
+  linear_logits_kernel<<<(unsigned)((rows + 127) / 128), 128, (size_t)(n_classes * C + n_classes) * sizeof(float), stream>>>(
+      code, ld_code, C, W, bias, n_classes, logits_scratch, rows);
+  STEGO_CHECK_LAUNCH("linear_logits_kernel");
+  LinearCEParams p;
+  p.logits = logits_scratch; p.label = label; p.B = B; p.h = h; p.w = w; p.H = H; p.W = Wimg; p.n = n_classes;
+  p.dlogits = dlogits_scratch; p.partials = partials_scratch;
+  const long long total = 1ll * B * H * Wimg;
+  long long g = (total + 255) / 256;
+  const long long cap = 8ll * num_sms();
+  const int grid = (int)(g < cap ? g : cap);
+  linear_ce_kernel<<<grid, 256, 0, stream>>>(p);
+  STEGO_CHECK_LAUNCH("linear_ce_kernel");
+  linear_ce_finish_kernel<<<1, 256, 0, stream>>>(partials_scratch, grid, loss_out);
+  STEGO_CHECK_LAUNCH("linear_ce_finish_kernel");
+  if (dlogits_scratch) {
+    const int rpb = 256;
+    dim3 wg(n_classes, (unsigned)((rows + rpb - 1) / rpb));
+    linear_wgrad_kernel<<<wg, 128, 0, stream>>>(dlogits_scratch, code, ld_code, C, n_classes, rows, rpb, loss_out,
+                                                grad_loss, dW, db);
+    STEGO_CHECK_LAUNCH("linear_wgrad_kernel");
+  }
+  return STEGO_OK;
+}

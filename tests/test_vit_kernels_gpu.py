@@ -18,7 +18,7 @@ def test_layernorm(cuda_dev, E):
     out = torch.empty(1000, E, device=cuda_dev, dtype=torch.bfloat16)
     ops.layernorm(x, g, b, out)
     want = torch.nn.functional.layer_norm(x, (E,), g, b, eps=1e-6)
-    assert (out.float() - want).abs().max().item() < 0.03
+    assert ((out.float() - want).abs() / (want.abs() + 1.0)).max().item() < 8e-3  # bf16 output rounding
     assert _rel(out, want) < 4e-3
 
 
@@ -40,7 +40,9 @@ def test_patchify_matches_conv(cuda_dev):
     img = torch.randn(2, 3, 32, 48, device=cuda_dev)
     w = torch.randn(16, 3, 8, 8, device=cuda_dev)
     rows = ops.patchify(img, 8)
+    torch.backends.cuda.matmul.allow_tf32 = False
     got = rows.float() @ w.reshape(16, -1).t()
+    torch.backends.cudnn.allow_tf32 = False
     want = torch.nn.functional.conv2d(img.bfloat16().float(), w, stride=8).flatten(2).transpose(1, 2).reshape(-1, 16)
     assert _rel(got, want) < 1e-5
 
