@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — STEGO correspondence-distillation training step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one full training step of the hot path on one synthetic batch per GPU: 2x frozen DINO ViT
+forward, seg head fwd/bwd, correspondence loss fwd/bwd (self + KNN + 5 random negatives), linear + cluster
+probes fwd/bwd, one gradient all-reduce (N > 1), three fused Adam updates.  Nothing is skipped or cached.
+
+One JSON line on rank 0:
+  value      images/s, whole job, inputs already resident in HBM (device timed, CUDA events, max over ranks)
+  e2e        same metric through the public API with pinned-host inputs copied H2D and the loss read back
+             D2H inside the timed region, every step
+  roofline   the dominant kernel of the step, timed live with CUDA events; achieved = algorithmic FLOPs/launch
+             / measured duration; peak from MEASURED_PEAKS.json (burst figure: kernel timed alone)
+  corr_roofline  the named correlation+loss kernel against BOTH the bf16 tensor peak and the HBM peak
+  cpu_baseline   the oracle port (CPU restatement of the reference, oracle/stego_oracle.py) on the host cores,
+                 bounded sample
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1..3]; batch is PER GPU (reference DDP semantics: DataLoader batch_size per process)
+    "c1": dict(model_type="vit_small", res=224, batch=32, desc="ViT-S/8 224x224 batch=32/GPU self+knn+5 random, bf16"),
+    "c2": dict(model_type="vit_base", res=320, batch=32, desc="ViT-B/8 320x320 batch=32/GPU, bf16"),
+    "c3": dict(model_type="vit_base", res=448, batch=16, desc="ViT-B/8 448x448 batch=16/GPU, bf16"),
+}
+N_CLASSES = 27
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# algorithmic work
+# ----------------------------------------------------------------------------------------------------
+def vit_dims(model_type, res):
+    E, heads = (384, 6) if model_type == "vit_small" else (768, 12)
+    hw = (res // 8) ** 2
+    return E, heads, hw, hw + 1
+
+
+def step_flops_per_image(model_type, res):
+    E, heads, hw, N = vit_dims(model_type, res)
+    gemm = 12 * (2 * N * E * 3 * E + 2 * N * E * E + 2 * 2 * N * E * 4 * E)
+    attn = 12 * (2 * 2 * N * N * E)
+    patch = 2 * hw * 192 * E
+    vit = gemm + attn + patch
+    D = 70
+    head_fwd = 2 * hw * E * D * 2 + 2 * hw * E * E
+    head_bwd = 2 * hw * E * D * 2 + 2 * hw * E * E * 2 + 2 * hw * D * E
+    corr = 7 * 2 * 121 * 121 * E + 3 * 7 * 2 * 121 * 121 * D
+    return 2 * vit + 2 * (head_fwd + head_bwd) + corr
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference step on the host cores (bounded sample)
+# ----------------------------------------------------------------------------------------------------
+def cpu_step_fn(model_type, res, batch):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stego_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    E = 384 if model_type == "vit_small" else 768
+    sd = O.vit_random_state(model_type, 8, seed=0)
+    hp = {k: v.requires_grad_(True) for k, v in O.head_random_state(E, 70, seed=1).items()}
+    g = torch.Generator().manual_seed(2)
+    probes = {"linear_probe.weight": (torch.randn(N_CLASSES, 70, 1, 1, generator=g) * 0.1).requires_grad_(True),
+              "linear_probe.bias": torch.zeros(N_CLASSES, requires_grad=True),
+              "cluster_probe.clusters": torch.randn(N_CLASSES, 70, generator=g).requires_grad_(True)}
+    params = list(hp.values()) + list(probes.values())
+    lrs = [5e-4] * len(hp) + [5e-3] * len(probes)  # train_segmentation.py:379-381
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    cfg = O.LossCfg()
+    img = torch.randn(batch, 3, res, res, generator=g)
+    img_pos = torch.randn(batch, 3, res, res, generator=g)
+    label = torch.randint(-1, N_CLASSES, (batch, res, res), generator=g)
+    it = [0]
+
+    def step():
+        it[0] += 1
+        with torch.no_grad():
+            f = O.vit_image_feat(sd, img, model_type, 8)
+            fp = O.vit_image_feat(sd, img_pos, model_type, 8)
+        masks = [O.draw_dropout2d_mask(batch, E) for _ in range(3)]
+        masks_pos = [O.draw_dropout2d_mask(batch, E) for _ in range(3)]
+        c1, c2, perms = O.draw_loss_randomness(batch, cfg)
+        out = O.training_losses(f, fp, hp, probes, label, masks, masks_pos, c1, c2, perms, cfg, N_CLASSES)
+        for p in params:
+            p.grad = None
+        out["total"].backward()
+        with torch.no_grad():
+            for p, (m, v), lr in zip(params, state, lrs):
+                O.adam_step(p, p.grad, m, v, it[0], lr)
+        return float(out["total"].detach())
+
+    return step, torch.get_num_threads()
+
+
+def time_cpu(model_type, res, batch, steps, warmup, budget_s=150.0):
+    """Returns (images/s, s/step, threads, steps actually timed); the step count is capped so that the
+    whole CPU leg stays within `budget_s` seconds."""
+    step, cores = cpu_step_fn(model_type, res, batch)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        if first * 2 < budget_s / 4:
+            step()
+    steps = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt, cores, steps
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-kernel timing (roofline)
+# ----------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters=10, flush=None):
+    """Average device time of fn() in ms: CUDA events on the launching (current) stream, L2 flushed between."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)  # > L2 (126 MB) write: evicts the previous iteration's working set
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / iters
+
+
+def kernel_rooflines(cfgd, peaks, dev):
+    """Time the step's main kernels in isolation at the bench shapes."""
+    from stego_b200 import corr, ops
+    from stego_b200.config import make_cfg
+    model_type, res, Bq = cfgd["model_type"], cfgd["res"], cfgd["batch"]
+    E, heads, hw, N = vit_dims(model_type, res)
+    B2 = 2 * Bq  # img ++ img_pos share one ViT pass
+    M = B2 * N
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)  # 256 MB
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    x_bf = rnd(M, E).bfloat16()
+    out = {}
+
+    def gemm_case(name, Nn, K, **kw):
+        a = rnd(M, K).bfloat16()
+        w = (rnd(Nn, K) * K ** -0.5).bfloat16()
+        bias = rnd(Nn)
+        o = torch.empty(M, Nn, device=dev, dtype=torch.float32 if kw.get("residual") else torch.bfloat16)
+        res_ = o if kw.get("residual") else None
+        act = kw.get("act", 0)
+        ms = time_kernel(lambda: ops.gemm(a, w, o, M=M, N=Nn, K=K, bias=bias, act=act, residual=res_), flush=flush)
+        fl = 2.0 * M * Nn * K
+        by = M * K * 2 + Nn * K * 2 + M * Nn * (8 if res_ is not None else 2)
+        out[name] = dict(ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, flops=fl, bytes=by, launches_per_step=12)
+
+    gemm_case("gemm_qkv", 3 * E, E)
+    gemm_case("gemm_proj", E, E, residual=True)
+    gemm_case("gemm_fc1_gelu", 4 * E, E, act=1)
+    gemm_case("gemm_fc2", E, 4 * E, residual=True)
+    qkv = rnd(M, 3 * E).bfloat16()
+    ao = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+    ms = time_kernel(lambda: ops.attention(qkv, ao, B2, N, E, heads), flush=flush)
+    fl = 2.0 * 2 * B2 * N * N * E
+    out["attention"] = dict(ms=ms, tflops=fl / ms / 1e9, gbs=(M * 4 * E * 2) / ms / 1e6, flops=fl, bytes=M * 4 * E * 2,
+                            launches_per_step=12)
+    xr = rnd(M, E)
+    gam, bet = rnd(E), rnd(E)
+    ms = time_kernel(lambda: ops.layernorm(xr, gam, bet, x_bf), flush=flush)
+    out["layernorm"] = dict(ms=ms, gbs=(M * E * 6) / ms / 1e6, bytes=M * E * 6, launches_per_step=25)
+
+    # correlation + loss (the BASELINE.json-named kernel): tiles -> fd/cd einsums -> loss partials
+    cfg = make_cfg()
+    spec = corr.LossSpec(cfg)
+    h = res // 8
+    feats = rnd(Bq, h, h, E).bfloat16().permute(0, 3, 1, 2)
+    feats_pos = rnd(Bq, h, h, E).bfloat16().permute(0, 3, 1, 2)
+    code = rnd(Bq, h, h, 72)[..., :70].permute(0, 3, 1, 2)
+    code_pos = rnd(Bq, h, h, 72)[..., :70].permute(0, 3, 1, 2)
+    c1, c2 = torch.rand(Bq, 11, 11, 2, device=dev) * 2 - 1, torch.rand(Bq, 11, 11, 2, device=dev) * 2 - 1
+    perms = torch.stack([torch.randperm(Bq, device=dev) for _ in range(5)])
+    ft = corr.build_tiles(feats, feats_pos, c1, c2, perms, spec, E)
+    ct = corr.build_tiles(code, code_pos, c1, c2, perms, spec, corr.CODE_PAD)
+    from stego_b200 import _lib
+    partials = torch.empty(7, Bq, 8, device=dev)
+    stats = torch.empty(7, 4, device=dev)
+    soc, shf = corr._i32(spec.slot_of_call), corr._f32(spec.shifts)
+
+    def corr_fwd():
+        _lib.check(_lib.load().stego_corr_loss_fwd(_lib.ptr(ft), _lib.ptr(ct), Bq, 11, E, 70, 7, 7, soc, shf, 1, 1, 0,
+                                                   _lib.ptr(partials), _lib.ptr(stats), 0, 0, 0, _lib.stream()), "corr_fwd")
+
+    ms = time_kernel(corr_fwd, flush=flush)
+    S = 121
+    fl = Bq * (7 * 2 * S * S * E + 7 * 2 * S * S * 70)  # fd + cd forward einsums (algorithmic)
+    by = Bq * (2 * hw * E * 2 + 2 * hw * 70 * 2)         # feats, feats_pos, code, code_pos once (bf16 algorithmic)
+    out["corr_loss_fwd"] = dict(ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, flops=fl, bytes=by, launches_per_step=1)
+    ms = time_kernel(lambda: corr.build_tiles(feats, feats_pos, c1, c2, perms, spec, E), flush=flush)
+    out["sample_norm_feats"] = dict(ms=ms, gbs=(Bq * 2 * hw * E * 2) / ms / 1e6, bytes=Bq * 2 * hw * E * 2,
+                                    launches_per_step=1)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
+    args = ap.parse_args()
+    cfgd = dict(CONFIGS[args.config])
+    if args.batch:
+        cfgd["batch"] = args.batch
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    model_type, res, B = cfgd["model_type"], cfgd["res"], cfgd["batch"]
+    workload = f"{args.config}: {cfgd['desc']}; synthetic N(0,1) images, random-init weights"
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path (oracle port), rank 0 only, bounded sample per step
+        if rank != 0:
+            return
+        sample_b = 2
+        v, dt, cores, nst = time_cpu(model_type, res, sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
+        print(json.dumps({
+            "impl": "reference", "metric": "train-step images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": nst, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": sample_b, "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"batch {sample_b} per step of the {args.config} workload (full step: 2x ViT fwd, "
+                                       "head, loss, probes, backward, Adam) with the oracle port on all host threads"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stego_b200 import _lib
+    from stego_b200.config import make_cfg
+    from stego_b200.segmenter import LitUnsupervisedSegmenter
+    cfg = make_cfg(model_type=model_type, res=res, batch_size=B, random_backbone_init=True)
+    torch.manual_seed(0)  # seed_everything(0) on every rank, like the reference (train_segmentation.py:403)
+    model = LitUnsupervisedSegmenter(N_CLASSES, cfg).to(dev)
+    model.train()
+    model.configure_optimizers()
+    gdata = torch.Generator().manual_seed(1000 + rank)  # data differs per rank
+    host = dict(img=torch.randn(B, 3, res, res, generator=gdata).pin_memory(),
+                img_pos=torch.randn(B, 3, res, res, generator=gdata).pin_memory(),
+                label=torch.randint(-1, N_CLASSES, (B, res, res), generator=gdata).pin_memory())
+    batch = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(nsteps, e2e):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(nsteps):
+            if e2e:
+                b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                loss = model.training_step(b, i)
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+            else:
+                model.training_step(batch, i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    run(args.warmup, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.load().stego_launch_count()
+    ms_dev = run(args.steps, False)
+    launches = _lib.load().stego_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    run(min(args.warmup, 3), True)
+    ms_e2e = run(args.steps, True)
+    loss_val = float(loss_host.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    img_per_step = B * world
+    value = img_per_step * args.steps / (ms_dev / 1e3)
+    e2e_value = img_per_step * args.steps / (ms_e2e / 1e3)
+    fl_img = step_flops_per_image(model_type, res)
+    line = {
+        "metric": "train-step images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": img_per_step, "per_gpu_batch": B, "res": res,
+                   "parallelism": f"dp{world}", "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; "
+                                                      "no explicit flush between steps"},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "last_loss": loss_val,
+        "step_tensor_roofline": {"flops_per_image": fl_img, "achieved_tflops": value / world * fl_img / 1e12,
+                                 "peak_tflops_sustained": peaks["tf_sust"],
+                                 "frac": value / world * fl_img / 1e12 / peaks["tf_sust"], "peak_source": peaks["source"]},
+    }
+    if not args.no_kernel_rooflines:
+        ks = kernel_rooflines(cfgd, peaks, dev)
+        step_ms = ms_dev / args.steps
+        for k, v in ks.items():
+            v["share_of_step"] = v["ms"] * v["launches_per_step"] / step_ms
+        dom = max((k for k in ks if "tflops" in ks[k] and k != "corr_loss_fwd"), key=lambda k: ks[k]["share_of_step"])
+        d = ks[dom]
+        line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peaks["tf_burst"],
+                            "unit": "TFLOP/s", "frac": d["tflops"] / peaks["tf_burst"], "traffic": None,
+                            "algorithmic_flops_per_launch": d["flops"], "ms_per_launch": d["ms"],
+                            "share_of_step": d["share_of_step"], "peak_source": peaks["source"] + ", burst"}
+        c = ks["corr_loss_fwd"]
+        line["corr_roofline"] = {"kernel": "corr_loss_fwd (fd+cd einsums + loss reduction, 7 calls x B images)",
+                                 "ms_per_launch": c["ms"], "achieved_tflops": c["tflops"],
+                                 "frac_of_bf16_tensor_peak": c["tflops"] / peaks["tf_burst"],
+                                 "achieved_gbs_algorithmic": c["gbs"], "frac_of_hbm_peak": c["gbs"] / peaks["hbm"],
+                                 "bound": "hbm/latency (S=121: intensity << ridge, SURVEY.md §8d)"}
+        line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()
+                               if kk in ("ms", "tflops", "gbs", "share_of_step")} for k, v in ks.items()}
+    if not args.no_cpu_baseline:
+        v, dt, cores, nst = time_cpu(model_type, res, 2, 3, 1, budget_s=30.0)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{nst} steps of batch 2 of the {args.config} workload with the oracle port "
+                                          f"(full step incl. 2x ViT fwd) on {cores} host threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

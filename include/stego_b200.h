@@ -30,6 +30,8 @@ extern "C" {
  * ---------------------------------------------------------------------------------------------- */
 STEGO_API int stego_version(void);
 STEGO_API const char* stego_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+STEGO_API long long stego_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction (tcgen05 + TMA + TMEM):

@@ -1,5 +1,6 @@
 #include "host_util.h"
 
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -19,6 +20,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
   return STEGO_ERR_CUDA;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached = 0;
@@ -92,3 +97,4 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 extern "C" const char* stego_last_error(void) { return stego::g_err; }
 extern "C" int stego_version(void) { return 100; }
+extern "C" long long stego_launch_count(void) { return stego::launch_count(); }

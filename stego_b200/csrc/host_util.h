@@ -18,6 +18,7 @@ enum : int {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);  // records the message, returns STEGO_ERR_CUDA
 int num_sms();
+void count_launch();  // bumps the library-wide kernel launch counter (stego_launch_count)
 
 // Encode a tiled bf16 tensor map (rank 2 or 3) with 128-byte swizzle.
 //   dims[i], box[i]: element counts, innermost first; strides_bytes[i]: byte stride of dim i+1.
@@ -36,6 +37,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   do {                                                               \
     cudaError_t _e = cudaGetLastError();                             \
     if (_e != cudaSuccess) return ::stego::cuda_fail(_e, what);      \
+    ::stego::count_launch();                                         \
   } while (0)
 
 }  // namespace stego

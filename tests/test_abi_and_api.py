@@ -1,0 +1,113 @@
+"""CPU: the C-ABI library loads and exports every symbol include/stego_b200.h declares; argument
+validation works without a GPU; the Python API mirrors the reference's `modules.py` surface and fails
+loudly (no CPU fallback) when asked to compute off-device."""
+import ctypes
+import inspect
+import os
+import sys
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from stego_b200 import _lib
+    protos = _lib.header_prototypes()
+    assert len(protos) >= 19
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), f"{name} declared in include/stego_b200.h but not exported"
+    assert _lib.load().stego_version() >= 100
+
+
+def test_bad_arguments_are_rejected_before_any_cuda_call():
+    from stego_b200 import _lib
+    lib = _lib.load()
+    rc = lib.stego_gemm_bf16(0, 8, 0, 0, 8, 0, 128, 128, 64, 0, 128, 0, 0, 0, 0, 0, 0, 1, 0, 0)
+    assert rc == -1 and "null pointer" in _lib.last_error()
+    rc = lib.stego_attention_fwd(16, 16, 1, 10, 100, 2, 0)
+    assert rc == -1 and "head_dim" in _lib.last_error()
+    rc = lib.stego_layernorm_bf16(16, 16, 16, 16, 4, 100, 1e-6, 0, 0)
+    assert rc == -2 and "unsupported" in _lib.last_error()
+
+
+def test_modules_surface_matches_reference():
+    from stego_b200 import modules as M
+    for name in ["LambdaLayer", "DinoFeaturizer", "ResizeAndClassify", "ClusterLookup", "FeaturePyramidNet",
+                 "DoubleConv", "norm", "average_norm", "tensor_correlation", "sample", "super_perm",
+                 "sample_nonzero_locations", "ContrastiveCorrelationLoss", "Decoder", "NetWithActivations",
+                 "ContrastiveCRFLoss"]:
+        assert hasattr(M, name), name
+    assert list(inspect.signature(M.DinoFeaturizer.forward).parameters) == ["self", "img", "n", "return_class_feat"]
+    assert list(inspect.signature(M.ContrastiveCorrelationLoss.forward).parameters) == [
+        "self", "orig_feats", "orig_feats_pos", "orig_salience", "orig_salience_pos", "orig_code", "orig_code_pos"]
+    assert list(inspect.signature(M.ClusterLookup.forward).parameters) == ["self", "x", "alpha", "log_probs"]
+    assert list(inspect.signature(M.FeaturePyramidNet.__init__).parameters) == [
+        "self", "granularity", "cut_model", "dim", "continuous"]
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    from stego_b200.config import make_cfg
+    from stego_b200.segmenter import LitUnsupervisedSegmenter
+    torch.manual_seed(0)
+    m = LitUnsupervisedSegmenter(27, make_cfg(random_backbone_init=True))
+    keys = set(m.state_dict().keys())
+    vit = {k for k in keys if k.startswith("net.model.")}
+    assert len(vit) == 150  # 150 ViT keys
+    for k in ["net.model.cls_token", "net.model.pos_embed", "net.model.patch_embed.proj.weight",
+              "net.model.blocks.11.attn.qkv.bias", "net.model.blocks.0.mlp.fc2.weight", "net.model.norm.bias",
+              "net.cluster1.0.weight", "net.cluster1.0.bias", "net.cluster2.0.weight", "net.cluster2.2.bias",
+              "train_cluster_probe.clusters", "cluster_probe.clusters", "linear_probe.weight", "linear_probe.bias",
+              "decoder.weight", "decoder.bias"]:
+        assert k in keys, k
+    assert m.net.n_feats == 384 and m.net.model.pos_embed.shape == (1, 785, 384)
+    n_train = sum(p.numel() for n, p in m.named_parameters() if p.requires_grad and n.startswith("net."))
+    assert n_train == 201740  # cluster1 + cluster2 for ViT-S
+    assert sum(p.numel() for p in m.net.model.parameters()) == 21670272
+
+
+def test_hot_path_refuses_cpu_tensors():
+    from stego_b200 import modules as M
+    from stego_b200.config import make_cfg
+    cfg = make_cfg(random_backbone_init=True)
+    loss = M.ContrastiveCorrelationLoss(cfg)
+    f, c = torch.randn(2, 384, 4, 4), torch.randn(2, 70, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss(f, f, None, None, c, c)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.ClusterLookup(70, 27)(c, None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.tensor_correlation(f, f)
+    with pytest.raises(ValueError):
+        M.DinoFeaturizer(70, make_cfg(model_type="vit_huge"))
+
+
+def test_rng_helpers_follow_reference_stream():
+    """super_perm / coordinate draws consume the torch generator exactly like the reference code."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stego_oracle as O
+    from stego_b200 import modules as M
+    from stego_b200.config import make_cfg
+    cfg = make_cfg()
+    lossfn = M.ContrastiveCorrelationLoss(cfg)
+    torch.manual_seed(99)
+    c1, c2 = lossfn.draw_coords(torch.zeros(2, 384, 28, 28), None, None)
+    perms = [M.super_perm(2, torch.device("cpu")) for _ in range(5)]
+    torch.manual_seed(99)
+    w1, w2, wp = O.draw_loss_randomness(2, O.LossCfg())
+    assert torch.equal(c1, w1) and torch.equal(c2, w2) and all(torch.equal(a, b) for a, b in zip(perms, wp))
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "super_perm.pt"))
+    for size, want in zip((1, 2, 5, 16, 32), g["draws"]):
+        torch.manual_seed(1000 + size)
+        assert torch.equal(torch.stack([M.super_perm(size, torch.device("cpu")) for _ in range(3)]), want)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from stego_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.load()

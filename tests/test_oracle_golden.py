@@ -1,0 +1,116 @@
+"""CPU: the oracle against the golden fixtures produced by the REAL reference (oracle/make_golden.py),
+and against the reference itself when /root/reference is present (build container)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import stego_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name))
+
+
+def _kat_inputs():
+    torch.manual_seed(1234)
+    return (torch.randn(2, 384, 28, 28), torch.randn(2, 384, 28, 28), torch.randn(2, 70, 28, 28),
+            torch.randn(2, 70, 28, 28))
+
+
+def test_kat_c0_known_answers():
+    """SURVEY.md §4.3 known-answer values."""
+    g = _load("corr_kat_c0.pt")
+    feats, feats_pos, code, code_pos = _kat_inputs()
+    code.requires_grad_(True)
+    code_pos.requires_grad_(True)
+    cfg = O.LossCfg()
+    torch.manual_seed(99)
+    c1, c2, perms = O.draw_loss_randomness(2, cfg)
+    assert torch.equal(c1, g["coords1"]) and torch.equal(c2, g["coords2"]) and torch.equal(torch.stack(perms), g["perms"])
+    out = O.correlation_loss(feats, feats_pos, code, code_pos, c1, c2, perms, cfg)
+    total = .67 * out[0] + .25 * out[2] + .63 * out[4].mean()
+    total.backward()
+    assert abs(out[0].item() - 0.0001824702339945361) < 2e-8
+    assert abs(out[2].item() - 0.005728472955524921) < 2e-8
+    assert abs(out[4].mean().item() - 0.022114580497145653) < 2e-8
+    assert abs(total.item() - 0.015486558899283409) < 2e-8
+    assert torch.allclose(torch.stack([out[1].mean(), out[3].mean(), out[5].mean()]), g["cd_means"], atol=1e-8)
+    assert abs(code.grad.norm().item() - 0.000311240553855896) < 1e-9
+    assert abs(code_pos.grad.norm().item() - 2.0298446543165483e-05) < 1e-10
+    assert torch.allclose(code.grad.reshape(-1)[::97], g["code_grad_sub"], atol=1e-10)
+    assert torch.allclose(code_pos.grad.reshape(-1)[::97], g["code_pos_grad_sub"], atol=1e-11)
+    assert torch.allclose(out[1].reshape(-1)[::211], g["intra_cd_sub"], atol=1e-6)
+    assert torch.allclose(out[4].reshape(-1)[::211], g["neg_loss_sub"], atol=1e-6)
+    assert out[1].shape == (2, 11, 11, 11, 11) and out[4].shape == (10, 11, 11, 11, 11)
+
+
+def test_small_case_full_gradients():
+    g = _load("corr_small.pt")
+    cfg = O.LossCfg()
+    code, code_pos = g["code"].clone().requires_grad_(True), g["code_pos"].clone().requires_grad_(True)
+    out = O.correlation_loss(g["feats"], g["feats_pos"], code, code_pos, g["coords1"], g["coords2"], list(g["perms"]), cfg)
+    total = O.weighted_correspondence_loss(out, cfg)
+    total.backward()
+    assert abs(total.item() - g["total"].item()) < 1e-6 * abs(g["total"].item()) + 1e-8
+    assert torch.allclose(code.grad, g["code_grad"], rtol=1e-4, atol=1e-9)
+    assert torch.allclose(code_pos.grad, g["code_pos_grad"], rtol=1e-4, atol=1e-9)
+    assert torch.allclose(out[3].reshape(-1)[::53], g["inter_cd_sub"], atol=1e-6)
+
+
+def test_cluster_lookup_kat():
+    g = _load("cluster_lookup_kat.pt")
+    torch.manual_seed(7)
+    _ = torch.randn(27, 70)  # ClusterLookup.__init__ draws the centroids first
+    x = torch.randn(2, 70, 28, 28)
+    loss, probs = O.cluster_lookup(x, g["clusters"], None)
+    assert abs(loss.item() - (-0.23893260955810547)) < 1e-7
+    assert int(probs.argmax(1).sum()) == 20458
+    assert torch.equal(probs.argmax(1).to(torch.int16), g["argmax"])
+    lp = O.cluster_lookup(x, g["clusters"], 2.0, log_probs=True)
+    assert abs(lp.sum().item() - g["log_probs_sum"].item()) < 0.5  # sum of 42k terms of magnitude ~3.3
+    assert torch.allclose(lp.reshape(-1)[::101], g["log_probs_sub"], atol=1e-5)
+
+
+def test_vit_tokens_golden():
+    g = _load("vit_small8_32px.pt")
+    sd = O.perturb_vit_state(O.vit_random_state("vit_small", 8, seed=3))
+    torch.manual_seed(11)
+    img = torch.randn(2, 3, 32, 32)
+    with torch.no_grad():
+        tok = O.vit_forward(sd, img, "vit_small", 8)
+    assert tok.shape == g["tokens"].shape == (2, 17, 384)
+    assert torch.allclose(tok, g["tokens"], atol=2e-5)
+
+
+def test_super_perm_golden():
+    g = _load("super_perm.pt")
+    for size, want in zip((1, 2, 5, 16, 32), g["draws"]):
+        torch.manual_seed(1000 + size)
+        got = torch.stack([O.super_perm_from_randperm(torch.randperm(size, dtype=torch.long)) for _ in range(3)])
+        assert torch.equal(got, want)
+    assert O.super_perm_from_randperm(torch.tensor([0])).tolist() == [0]
+
+
+def test_sample_semantics_probe():
+    """3x4 ramp, corner coords -> [0, 8, 3, 11] (grid permutation, x->width, y->height)."""
+    t = torch.arange(12.).reshape(1, 1, 3, 4)
+    coords = torch.tensor([[[[-1., -1.], [1., -1.]], [[-1., 1.], [1., 1.]]]])
+    assert O.bilinear_sample(t, coords).reshape(-1).tolist() == [0., 8., 3., 11.]
+
+
+def test_clamp_gradient_is_inclusive():
+    x = torch.tensor([0.0, -1e-6, 1e-6], requires_grad=True)
+    x.clamp(0.0).sum().backward()
+    assert x.grad.tolist() == [1.0, 0.0, 1.0]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree only exists in the build container")
+def test_oracle_matches_real_reference():
+    import check_against_reference
+    assert check_against_reference.run_checks()
