@@ -1,0 +1,43 @@
+"""Launch the step's main kernels once each at the c1 bench shapes (for `ncu --set full`).
+    ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16|attention_fwd|corr_kernel' \
+        -o gpurun_out/prof python profiles/prof_kernels.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from stego_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+which = sys.argv[1:] or ["qkv", "proj", "fc1", "fc2", "attn"]
+E, heads, N, B2 = 384, 6, 785, 64
+M = B2 * N
+
+
+def gemm(Nn, K, act=0, residual=False):
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(Nn, K, device=dev) * K ** -0.5).bfloat16()
+    bias = torch.randn(Nn, device=dev)
+    o = torch.zeros(M, Nn, device=dev, dtype=torch.float32 if residual else torch.bfloat16)
+    for _ in range(2):
+        ops.gemm(a, w, o, M=M, N=Nn, K=K, bias=bias, act=act, residual=o if residual else None)
+
+
+if "qkv" in which:
+    gemm(3 * E, E)
+if "proj" in which:
+    gemm(E, E, residual=True)
+if "fc1" in which:
+    gemm(4 * E, E, act=1)
+if "fc2" in which:
+    gemm(E, 4 * E, residual=True)
+if "attn" in which:
+    qkv = torch.randn(M, 3 * E, device=dev).bfloat16()
+    ao = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.attention(qkv, ao, B2, N, E, heads)
+torch.cuda.synchronize()
+print("done")

@@ -8,10 +8,10 @@
 //   * segmentation head (reference: src/modules.py:73-81 cluster1/cluster2 1x1 convs) forward,
 //     dgrad (B operand MN-major) and wgrad (both operands MN-major, split-K + fp32 atomics).
 //
-// Structure: persistent CTAs (one per SM), 192 threads:
+// Structure: persistent CTAs (one per SM), 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM, 2 buffers)
-//   warps 2..5  epilogue       (tcgen05.ld TMEM->regs, bias/GELU/ReLU/residual, vectorised global stores)
+//   warps 2..9  epilogue       (tcgen05.ld TMEM->regs, bias/GELU/ReLU/residual, smem transpose, coalesced stores)
 // Operand tiles are 128 x 64 (A) and BN x 64 (B) bf16; accumulation fp32.
 #include "common.cuh"
 #include "host_util.h"
@@ -20,7 +20,7 @@ namespace stego {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct GemmParams {
   int M, N, K;        // logical GEMM sizes; K is the reduction length
@@ -36,9 +36,22 @@ struct GemmParams {
   int row_div;        // >0: patch-embed mode: out_row = r + r/row_div + 1, residual row = r % row_div + 1
   int atomic;         // 1: fp32 atomicAdd into out (split-K)
   int vec_ok;         // host-verified 16-byte alignment of out/residual rows
+  int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU, nn.GELU default.  erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one rcp + one ex2 on
+// the MUFU pipe and ~10 FMAs instead of the ~25-instruction erff — the fc1 epilogue is issue-bound otherwise.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 template <int BN, int kStages, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -52,7 +65,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  constexpr uint32_t EPI_BYTES = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
+  uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -75,7 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -153,8 +168,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue warps (2..9) =====================
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate column groups
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tn = (t / p.splits) % tiles_n;
@@ -169,8 +185,120 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         res_row = row % p.row_div + 1;
       }
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (p.fast_epi) {
+        // ---- coalesced epilogue: TMEM -> regs (bias/act) -> per-warp swizzled smem transpose -> 128-byte row
+        //      segments: every global load/store instruction covers 4 full rows x 128 B.
+        uint8_t* buf = epi_smem + (warp - 2) * 4096;
+        const int row_base = tm * GEMM_BM + quarter * 32;
+        const int rsub = lane >> 3, chunk = lane & 7;
+        if (p.out_bf16) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+          for (int c = half; c < BN / 64; c += 2) {
+            const int col0 = tn * BN + c * 64;
+            if (col0 >= p.N) break;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + c * 64, v0);
+            tmem_ld32(taddr + c * 64 + 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t* v = hh ? v1 : v0;
+              const int cb = col0 + hh * 32;
+              float x[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+              if (p.bias != nullptr && cb < p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
+                  x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                }
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+              } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+                w.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+                w.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+                w.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+                *reinterpret_cast<uint4*>(buf + sw128_offset(lane, hh * 4 + j)) = w;
+              }
+            }
+            __syncwarp();
+            const int col = col0 + chunk * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rsub;
+              const int grow = row_base + r;
+              if (grow < p.M && col < p.N) {
+                const uint4 w = *reinterpret_cast<const uint4*>(buf + sw128_offset(r, chunk));
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(grow) * p.ldo + col) = w;
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += 2) {
+            const int col0 = tn * BN + c * 32;
+            if (col0 >= p.N) break;
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + sw128_offset(lane, j)) =
+                  make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            __syncwarp();
+            const int col = col0 + chunk * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rsub;
+              const int grow = row_base + r;
+              if (grow < p.M && col < p.N) {
+                float4 y = *reinterpret_cast<const float4*>(buf + sw128_offset(r, chunk));
+                if (p.residual != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col);
+                  y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+                }
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + col) = y;
+              }
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = tn * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
@@ -257,7 +385,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int kStages, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 256;
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * 4096 + 1024 + 256;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
@@ -304,6 +432,13 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((size_t(ldo) * esz) % 16 == 0) &&
              (residual == nullptr || (((reinterpret_cast<uintptr_t>(residual) & 15u) == 0) && (size_t(ldr) * 4) % 16 == 0));
 
+  // the coalesced epilogue handles whole 32-column (fp32) / 64-column (bf16) groups: N % 32 == 0, bias 16B-aligned
+  p.fast_epi = p.vec_ok && !atomic_out && row_div == 0 && (N % 32 == 0) &&
+               (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
+               !(out_bf16 && residual != nullptr);
+  // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
+  const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
+
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -316,9 +451,10 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   {
     uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, b_mn_major ? 64u : 128u};
+    uint32_t box[2] = {64, b_mn_major ? 64u : (wide ? 256u : 128u)};
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
+  if (wide) return launch_gemm<256, 4, false, false>(tmA, tmB, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 6, false, false>(tmA, tmB, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 6, false, true>(tmA, tmB, p, stream);
   if (a_mn_major && b_mn_major) return launch_gemm<128, 6, true, true>(tmA, tmB, p, stream);

@@ -193,7 +193,8 @@ struct LinearCEParams {
   const long long* label;  // [B][H][W]
   int B, h, w, H, W, n;
   float* dlogits;        // [B*h*w][LP_LD] unnormalised gradient (atomics), or null (loss only)
-  float* partials;       // [gridDim.x][2]: loss sum, valid count
+  double* acc;           // [2]: loss sum, valid count (zeroed before the launch)
+  int tiles_y, tiles_x, box_h, box_w;
 };
 
 __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
@@ -201,81 +202,142 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   float s = scale * (dst + 0.5f) - 0.5f;
   if (s < 0.f) s = 0.f;
   i0 = static_cast<int>(s);
+  if (i0 > in_size - 1) i0 = in_size - 1;
   i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
   l1 = s - i0;
 }
 
+constexpr int LCE_TILE = 32;  // hi-res pixels per tile side
+
+// One CTA per 32x32 tile of output pixels.  The low-res logits the tile can touch (its "box") are staged in
+// shared memory, the upsample + softmax + CE runs per pixel in registers, and the gradient wrt the low-res
+// logits is accumulated in a shared-memory box: lanes of a warp are 32 x-adjacent pixels, runs of lanes that
+// share the same taps are combined with a segmented shuffle reduction so that only run leaders touch the
+// (shared-memory) atomics; the box is flushed to global with one atomic per touched element.
 __global__ void __launch_bounds__(256)
 linear_ce_kernel(LinearCEParams p) {
+  extern __shared__ float sm[];
+  const int box_cap = p.box_h * p.box_w;
+  float* slog = sm;
+  float* sgrad = sm + box_cap * LP_LD;
   __shared__ float sred[2][8];
-  const long long total = 1ll * p.B * p.H * p.W;
+  const int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  const int ty = (tile / p.tiles_x) % p.tiles_y;
+  const int b = tile / (p.tiles_x * p.tiles_y);
+  const int Y0 = ty * LCE_TILE, X0 = tx * LCE_TILE;
+  const int Yl = min(Y0 + LCE_TILE - 1, p.H - 1), Xl = min(X0 + LCE_TILE - 1, p.W - 1);
   const float sy = static_cast<float>(p.h) / p.H, sx = static_cast<float>(p.w) / p.W;
+  int by0, by1, bx0, bx1, tmp;
+  float ftmp;
+  src_index(Y0, sy, p.h, by0, tmp, ftmp);
+  src_index(Yl, sy, p.h, tmp, by1, ftmp);
+  src_index(X0, sx, p.w, bx0, tmp, ftmp);
+  src_index(Xl, sx, p.w, tmp, bx1, ftmp);
+  const int bh = by1 - by0 + 1, bw = bx1 - bx0 + 1;  // <= box_h, box_w by construction on the host
+  const long long base = 1ll * b * p.h * p.w;
+  for (int idx = threadIdx.x; idx < bh * bw * LP_LD; idx += blockDim.x) {
+    const int k = idx % LP_LD, cell = idx / LP_LD;
+    const int r = cell / bw, c = cell % bw;
+    slog[idx] = (k < p.n) ? p.logits[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k] : 0.f;
+    sgrad[idx] = 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float lsum = 0.f, cnt = 0.f;
-  for (long long pix = 1ll * blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += 1ll * gridDim.x * blockDim.x) {
-    const long long lab = p.label[pix];
-    if (lab < 0 || lab >= p.n) continue;
-    const int X = static_cast<int>(pix % p.W);
-    const int Y = static_cast<int>((pix / p.W) % p.H);
-    const int b = static_cast<int>(pix / (1ll * p.W * p.H));
+  for (int row = warp; row < LCE_TILE; row += 8) {
+    const int Y = Y0 + row, X = X0 + lane;
+    const bool inb = (Y < p.H) && (X < p.W);
+    long long lab = -1;
+    if (inb) lab = p.label[(1ll * b * p.H + Y) * p.W + X];
+    const bool valid = inb && lab >= 0 && lab < p.n;
     int y0, y1, x0, x1;
     float ly, lx;
-    src_index(Y, sy, p.h, y0, y1, ly);
-    src_index(X, sx, p.w, x0, x1, lx);
+    src_index(min(Y, p.H - 1), sy, p.h, y0, y1, ly);
+    src_index(min(X, p.W - 1), sx, p.w, x0, x1, lx);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const long long base = 1ll * b * p.h * p.w;
-    const float* l00 = p.logits + (base + y0 * p.w + x0) * LP_LD;
-    const float* l01 = p.logits + (base + y0 * p.w + x1) * LP_LD;
-    const float* l10 = p.logits + (base + y1 * p.w + x0) * LP_LD;
-    const float* l11 = p.logits + (base + y1 * p.w + x1) * LP_LD;
+    const int c00 = ((y0 - by0) * bw + (x0 - bx0)) * LP_LD, c01 = ((y0 - by0) * bw + (x1 - bx0)) * LP_LD;
+    const int c10 = ((y1 - by0) * bw + (x0 - bx0)) * LP_LD, c11 = ((y1 - by0) * bw + (x1 - bx0)) * LP_LD;
     float z[LP_LD];
     float mx = -INFINITY;
-    for (int k = 0; k < p.n; ++k) {
-      z[k] = w00 * l00[k] + w01 * l01[k] + w10 * l10[k] + w11 * l11[k];
-      mx = fmaxf(mx, z[k]);
+#pragma unroll
+    for (int k = 0; k < LP_LD; ++k) {
+      if (k < p.n) {
+        z[k] = w00 * slog[c00 + k] + w01 * slog[c01 + k] + w10 * slog[c10 + k] + w11 * slog[c11 + k];
+        mx = fmaxf(mx, z[k]);
+      }
     }
     float se = 0.f;
-    for (int k = 0; k < p.n; ++k) se += expf(z[k] - mx);
+#pragma unroll
+    for (int k = 0; k < LP_LD; ++k)
+      if (k < p.n) se += expf(z[k] - mx);
     const float lse = mx + logf(se);
-    lsum += lse - z[lab];
-    cnt += 1.f;
+    if (valid) {
+      float zl = 0.f;
+#pragma unroll
+      for (int k = 0; k < LP_LD; ++k)
+        if (k == lab) zl = z[k];
+      lsum += lse - zl;
+      cnt += 1.f;
+    }
     if (p.dlogits) {
-      float* d00 = p.dlogits + (base + y0 * p.w + x0) * LP_LD;
-      float* d01 = p.dlogits + (base + y0 * p.w + x1) * LP_LD;
-      float* d10 = p.dlogits + (base + y1 * p.w + x0) * LP_LD;
-      float* d11 = p.dlogits + (base + y1 * p.w + x1) * LP_LD;
-      for (int k = 0; k < p.n; ++k) {
-        const float g = expf(z[k] - lse) - ((k == lab) ? 1.f : 0.f);
-        atomicAdd(d00 + k, g * w00);
-        atomicAdd(d01 + k, g * w01);
-        atomicAdd(d10 + k, g * w10);
-        atomicAdd(d11 + k, g * w11);
+      // lanes with identical (x0, x1) form contiguous runs (x is monotone in the lane index)
+      const int key = x0 * 2 + (x1 - x0);
+      const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool leader = (lane == 0) || (key_prev != key);
+      bool same[5];
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int d = 1 << s;
+        const int kd = __shfl_down_sync(0xffffffffu, key, d);
+        same[s] = (lane + d < 32) && (kd == key);
+      }
+#pragma unroll
+      for (int k = 0; k < LP_LD; ++k) {
+        if (k < p.n) {
+          const float g = valid ? (expf(z[k] - lse) - ((k == lab) ? 1.f : 0.f)) : 0.f;
+          float v0 = g * (1.f - lx), v1 = g * lx;  // x-weights; y-weights applied by the leader
+#pragma unroll
+          for (int s = 0; s < 5; ++s) {
+            const float a0 = __shfl_down_sync(0xffffffffu, v0, 1 << s);
+            const float a1 = __shfl_down_sync(0xffffffffu, v1, 1 << s);
+            if (same[s]) { v0 += a0; v1 += a1; }
+          }
+          if (leader && (v0 != 0.f || v1 != 0.f)) {
+            atomicAdd(&sgrad[c00 + k], v0 * (1.f - ly));
+            atomicAdd(&sgrad[c01 + k], v1 * (1.f - ly));
+            atomicAdd(&sgrad[c10 + k], v0 * ly);
+            atomicAdd(&sgrad[c11 + k], v1 * ly);
+          }
+        }
       }
     }
   }
   lsum = warp_sum(lsum);
   cnt = warp_sum(cnt);
-  if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = lsum; sred[1][threadIdx.x >> 5] = cnt; }
+  if (lane == 0) { sred[0][warp] = lsum; sred[1][warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f, c = 0.f;
+    double a = 0, c = 0;
     for (int w = 0; w < 8; ++w) { a += sred[0][w]; c += sred[1][w]; }
-    p.partials[2 * blockIdx.x] = a;
-    p.partials[2 * blockIdx.x + 1] = c;
+    if (c > 0) { atomicAdd(p.acc, a); atomicAdd(p.acc + 1, c); }
+  }
+  if (p.dlogits) {
+    for (int idx = threadIdx.x; idx < bh * bw * LP_LD; idx += blockDim.x) {
+      const float v = sgrad[idx];
+      if (v != 0.f) {
+        const int k = idx % LP_LD, cell = idx / LP_LD;
+        const int r = cell / bw, c = cell % bw;
+        atomicAdd(p.dlogits + (base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k, v);
+      }
+    }
   }
 }
 
 // out[0] = loss_sum / count ; out[1] = count
-__global__ void linear_ce_finish_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
-  __shared__ double sh[2][256];
-  double a = 0, c = 0;
-  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { a += partials[2 * i]; c += partials[2 * i + 1]; }
-  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = c;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { out[0] = static_cast<float>(sh[0][0] / sh[1][0]); out[1] = static_cast<float>(sh[1][0]); }
+__global__ void linear_ce_finish_kernel(const double* __restrict__ acc, float* __restrict__ out) {
+  out[0] = static_cast<float>(acc[0] / acc[1]);
+  out[1] = static_cast<float>(acc[1]);
 }
 
 // dW[k][c] += (gscale/count) * sum_r dlogits[r][k] code[r][c];  db[k] += (gscale/count) * sum_r dlogits[r][k]
@@ -387,14 +449,33 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   STEGO_CHECK_LAUNCH("linear_logits_kernel");
   LinearCEParams p;
   p.logits = logits_scratch; p.label = label; p.B = B; p.h = h; p.w = w; p.H = H; p.W = Wimg; p.n = n_classes;
-  p.dlogits = dlogits_scratch; p.partials = partials_scratch;
-  const long long total = 1ll * B * H * Wimg;
-  long long g = (total + 255) / 256;
-  const long long cap = 8ll * num_sms();
-  const int grid = (int)(g < cap ? g : cap);
-  linear_ce_kernel<<<grid, 256, 0, stream>>>(p);
+  p.dlogits = dlogits_scratch;
+  STEGO_CHECK_ARG((reinterpret_cast<uintptr_t>(partials_scratch) & 7u) == 0, "stego_linear_probe_ce: scratch not 8-byte aligned");
+  p.acc = reinterpret_cast<double*>(partials_scratch);
+  p.tiles_y = (H + LCE_TILE - 1) / LCE_TILE;
+  p.tiles_x = (Wimg + LCE_TILE - 1) / LCE_TILE;
+  p.box_h = (int)((double)LCE_TILE * h / H) + 3;
+  p.box_w = (int)((double)LCE_TILE * w / Wimg) + 3;
+  if (p.box_h > h) p.box_h = h;
+  if (p.box_w > w) p.box_w = w;
+  const size_t ce_smem = (size_t)2 * p.box_h * p.box_w * LP_LD * sizeof(float);
+  STEGO_CHECK_ARG(ce_smem <= 200 * 1024, "stego_linear_probe_ce: upsample ratio %dx%d -> %dx%d needs %zu B of smem", h, w, H, Wimg, ce_smem);
+  {
+    static size_t configured = 0;
+    if (ce_smem > 48 * 1024 && ce_smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_ce)");
+      configured = ce_smem;
+    }
+  }
+  {
+    cudaError_t e = cudaMemsetAsync(partials_scratch, 0, 2 * sizeof(double), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(linear_ce acc)");
+  }
+  const int grid = B * p.tiles_y * p.tiles_x;
+  linear_ce_kernel<<<grid, 256, ce_smem, stream>>>(p);
   STEGO_CHECK_LAUNCH("linear_ce_kernel");
-  linear_ce_finish_kernel<<<1, 256, 0, stream>>>(partials_scratch, grid, loss_out);
+  linear_ce_finish_kernel<<<1, 1, 0, stream>>>(p.acc, loss_out);
   STEGO_CHECK_LAUNCH("linear_ce_finish_kernel");
   if (dlogits_scratch) {
     const int rpb = 256;

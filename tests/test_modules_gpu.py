@@ -171,3 +171,23 @@ def test_training_step_matches_oracle(cuda_dev, arch, res, B):
         p = params0[k].clone()
         O.adam_step(p, grads[k], torch.zeros_like(p), torch.zeros_like(p), 1, 5e-4 if k.startswith("net.") else 5e-3)
         assert _rel(params1[k] - params0[k], p - params0[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("B,h,w,H,W", [(2, 28, 28, 224, 224), (3, 7, 9, 50, 61), (1, 12, 12, 12, 12), (2, 40, 40, 320, 320)])
+def test_linear_probe_ce_matches_oracle(cuda_dev, B, h, w, H, W):
+    import stego_oracle as O
+    from stego_b200.segmenter import linear_probe_ce
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    code = torch.randn(B, 70, h, w, generator=g)
+    weight = (torch.randn(27, 70, 1, 1, generator=g) * 0.3).requires_grad_(True)
+    bias = (torch.randn(27, generator=g) * 0.1).requires_grad_(True)
+    label = torch.randint(-1, 29, (B, H, W), generator=g)  # includes ignored labels (-1, 27, 28)
+    want = O.linear_probe_loss(code, weight, bias, label, 27)
+    gw, gb = torch.autograd.grad(want, [weight, bias])
+    wg = weight.detach().to(cuda_dev).requires_grad_(True)
+    bg = bias.detach().to(cuda_dev).requires_grad_(True)
+    cg = code.to(cuda_dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    got = linear_probe_ce(cg, wg, bg, label.to(cuda_dev))
+    ggw, ggb = torch.autograd.grad(got * 2.0, [wg, bg])
+    assert abs(got.item() - want.item()) < 1e-5 * abs(want.item()) + 1e-6
+    assert _rel(ggw, 2 * gw) < 1e-4 and _rel(ggb, 2 * gb) < 1e-4
