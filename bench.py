@@ -228,6 +228,10 @@ def kernel_rooflines(cfgd, peaks, dev):
     gemm_case("gemm_proj", E, E, residual=True)
     gemm_case("gemm_fc1_gelu", 4 * E, E, act=1)
     gemm_case("gemm_fc2", E, 4 * E, residual=True)
+    if os.environ.get("STEGO_BENCH_DIAG"):
+        gemm_case("diag_fc1_noact", 4 * E, E)
+        gemm_case("diag_proj_bf16out", E, E)
+        gemm_case("diag_fc2_bf16out", E, 4 * E)
     qkv = rnd(M, 3 * E).bfloat16()
     ao = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
     ms = time_kernel(lambda: ops.attention(qkv, ao, B2, N, E, heads), flush=flush)

@@ -10,7 +10,11 @@
 //   warp 0      TMA producer: Q tile once, then a 3-stage ring of (K,V) tiles
 //   warp 1      MMA issuer  : S_j = Q K_j^T (128x128x64), O_j = P_j V_j (128x64x128)
 //   warps 2..5  softmax warpgroup 0  (KV tiles 0,2,4,..)   } each thread owns one query row, keeps its own
-//   warps 6..9  softmax warpgroup 1  (KV tiles 1,3,5,..)   } running max / sum / fp32 output accumulator
+//   warps 6..9  softmax warpgroup 1  (KV tiles 1,3,5,..)   } reference max / running sum
+// O accumulates IN TMEM across a warpgroup's KV tiles (tcgen05.mma accumulate), so the softmax warps never wait
+// for P V inside the loop.  The running max is updated lazily (FA4-style): the reference max only moves when the
+// new row max exceeds it by more than 2^8, and only then is O rescaled in TMEM (tcgen05.ld -> scale ->
+// tcgen05.st); otherwise P = exp2(s - m_ref) is at most 256, harmless in bf16 / fp32.
 // The two warpgroups work on alternate KV tiles (S, P, O are double buffered) and are merged once at the
 // end (split-KV combine), so there is no cross-warpgroup dependency inside the loop.
 // Input is the packed qkv GEMM output [B, N, 3E] bf16 (q | k | v, head-major inside each), read through
@@ -54,8 +58,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   uint64_t* s_empty = s_full + 2;                 // [2]
   uint64_t* p_full = s_empty + 2;                 // [2]
   uint64_t* o_full = p_full + 2;                  // [2]
-  uint64_t* o_empty = o_full + 2;                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,7 +79,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       mbar_init(&s_empty[b], 4);
       mbar_init(&p_full[b], 4);
       mbar_init(&o_full[b], 1);
-      mbar_init(&o_empty[b], 4);
     }
     fence_barrier_init();
   }
@@ -116,8 +118,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         const int b = i & 1;
         const uint32_t it = static_cast<uint32_t>(i >> 1);
         const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
-        mbar_wait(&p_full[b], it & 1u);
-        mbar_wait(&o_empty[b], (it & 1u) ^ 1u);
+        mbar_wait(&p_full[b], it & 1u);  // P written (and O rescaled, if needed) by warpgroup b
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + ATT_SMEM_P + b * 2 * ATT_TILE_BYTES);
         const uint32_t sv = smem_u32(smem + ATT_SMEM_KV + stage_i * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
@@ -125,7 +126,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
           const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 8192, 1024);
-          umma_bf16(TM_O + b * 64, da, db, IDESC_O, kk > 0 ? 1u : 0u);
+          umma_bf16(TM_O + b * 64, da, db, IDESC_O, (it > 0 || kk > 0) ? 1u : 0u);  // accumulate over this WG's tiles
         }
         umma_commit(&o_full[b]);
         umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
@@ -157,11 +158,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const int r = quarter * 32 + lane;  // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* sp = smem + ATT_SMEM_P + wg * 2 * ATT_TILE_BYTES;
-    float acc[ATT_D];
-#pragma unroll
-    for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;  // m_run: reference max the exponentials are taken against
     const float c = p.scale_log2e;
+    const uint32_t to = TM_O + wg * 64 + lane_off;
 
     uint32_t it = 0;
     for (int j = wg; j < nkv; j += 2, ++it) {
@@ -185,8 +184,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             if (ch * 32 + t < valid) mx = fmaxf(mx, __uint_as_float(v[t]));
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float mc = m_new * c;
+      // lazy reference-max update: move it only on the first tile or when it is off by more than 2^8
+      const bool first = (it == 0);
+      const bool move = first || ((mx - m_run) * c > 8.0f);
+      float alpha = 1.0f;
+      if (move) {
+        alpha = first ? 0.0f : ex2_approx((m_run - mx) * c);
+        m_run = mx;
+        l_run *= alpha;
+      }
+      // P V of this warpgroup's previous tile must have retired before P is overwritten or O is touched
+      if (!first) {
+        mbar_wait(&o_full[wg], (it - 1u) & 1u);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, move)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(to + h * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
+            tmem_st32(to + h * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_run * c;
       // pass 2: p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem
       float rs = 0.f;
 #pragma unroll 1
@@ -197,15 +221,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         float e[32];
         if (valid >= ch * 32 + 32) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = exp2f(fmaf(__uint_as_float(v[t]), c, -mc));
+          for (int t = 0; t < 32; ++t) e[t] = ex2_approx(fmaf(__uint_as_float(v[t]), c, -mc));
         } else {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = (ch * 32 + t < valid) ? exp2f(fmaf(__uint_as_float(v[t]), c, -mc)) : 0.f;
+          for (int t = 0; t < 32; ++t) e[t] = (ch * 32 + t < valid) ? ex2_approx(fmaf(__uint_as_float(v[t]), c, -mc)) : 0.f;
         }
         uint8_t* blk = sp + (ch >> 1) * ATT_TILE_BYTES;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          // round to bf16 first and sum the ROUNDED values so that l matches what the MMA consumes
           uint4 w;
           w.x = pack_bf16x2(e[8 * g + 0], e[8 * g + 1]);
           w.y = pack_bf16x2(e[8 * g + 2], e[8 * g + 3]);
@@ -216,6 +239,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
           for (int t = 0; t < 8; ++t) rs += e[8 * g + t];
         }
       }
+      l_run += rs;
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
@@ -223,24 +247,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         mbar_arrive(&s_empty[wg]);
         mbar_arrive(&p_full[wg]);
       }
-      const float alpha = exp2f((m_run - m_new) * c);  // m_run = -inf on the first tile -> 0
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      // O_j = P_j V_j lands in TMEM; fold it into the running fp32 accumulator
-      mbar_wait(&o_full[wg], it & 1u);
+    }
+    // this warpgroup's O (sum over its KV tiles, relative to m_run) -> registers
+    float acc[ATT_D];
+    if (it > 0) {
+      mbar_wait(&o_full[wg], (it - 1u) & 1u);
       tc_fence_after();
-      const uint32_t to = TM_O + wg * 64 + lane_off;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
         tmem_ld32(to + h * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) acc[h * 32 + t] = fmaf(acc[h * 32 + t], alpha, __uint_as_float(v[t]));
+        for (int t = 0; t < 32; ++t) acc[h * 32 + t] = __uint_as_float(v[t]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[wg]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
     }
 
     // ---- combine the two warpgroups (split-KV merge) and write the output ----

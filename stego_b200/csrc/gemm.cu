@@ -43,13 +43,14 @@ struct GemmParams {
 // the MUFU pipe and ~10 FMAs instead of the ~25-instruction erff — the fc1 epilogue is issue-bound otherwise.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));  // MUFU.RCP, no Newton fix-up
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
+  const float erf_abs = fmaf(-poly, ex2_approx(-1.4426950408889634f * z * z), 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
@@ -175,6 +176,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tn = (t / p.splits) % tiles_n;
       const int tm = t / (p.splits * tiles_n);
+      if (p.fast_epi && p.residual != nullptr) {
+        // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
+        const int prow = tm * GEMM_BM + quarter * 32 + lane;
+        if (prow < p.M) {
+          for (int c = half; c < BN / 32; c += 2) {
+            const int pc = tn * BN + c * 32;
+            if (pc < p.N)
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.residual + static_cast<size_t>(prow) * p.ldr + pc));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = tm * GEMM_BM + quarter * 32 + lane;
