@@ -362,9 +362,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.load().stego_launch_count()
+    l0 = _lib.launch_count()
     ms_dev = run(args.steps, False)
-    launches = _lib.load().stego_launch_count() - l0
+    launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)
     ms_e2e = run(args.steps, True)

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libstego_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "stego_b200.h")
 
 _lib = None
+replayed_launches = 0  # kernels launched through CUDA-graph replays (not seen by stego_launch_count)
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -70,6 +71,11 @@ def load():
         fn.argtypes = [_CTYPES[a] for a in args]
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    """Kernels this library launched in this process: direct launches + launches inside replayed CUDA graphs."""
+    return int(load().stego_launch_count()) + replayed_launches
 
 
 def last_error() -> str:

@@ -26,18 +26,21 @@
 namespace stego {
 
 constexpr int ATT_BQ = 128;
-constexpr int ATT_BKV = 128;
+constexpr int ATT_BKV = 64;   // 64-key tiles: 6 % padding waste at N = 785 (128-key tiles waste 14 %), half the smem
 constexpr int ATT_D = 64;
 constexpr int ATT_STAGES = 3;
 constexpr int ATT_THREADS = 320;
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S: 2 x 64, O: 2 x 64 -> two CTAs fit the 512 columns of an SM
 
-constexpr uint32_t ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128][64] bf16 tile
+constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;   // 16 KB [128 q][64 d]
+constexpr uint32_t ATT_KV_BYTES = 64 * 64 * 2;   // 8 KB  [64 kv][64 d]
+constexpr uint32_t ATT_P_BYTES = 128 * 64 * 2;   // 16 KB [128 q][64 kv]
 constexpr uint32_t ATT_SMEM_Q = 0;
-constexpr uint32_t ATT_SMEM_KV = ATT_TILE_BYTES;                                   // stages x (K,V)
-constexpr uint32_t ATT_SMEM_P = ATT_SMEM_KV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 32 KB
-constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_P + 2 * 2 * ATT_TILE_BYTES;              // m,l of WG1: 2 x 128 floats
+constexpr uint32_t ATT_SMEM_KV = ATT_Q_BYTES;                                   // stages x (K,V)
+constexpr uint32_t ATT_SMEM_P = ATT_SMEM_KV + ATT_STAGES * 2 * ATT_KV_BYTES;    // one P tile per warpgroup
+constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_P + 2 * ATT_P_BYTES;                  // m,l of WG1: 2 x 128 floats
 constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_ML + 1024;
-constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256 + 1024;  // + alignment slack
+constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256 + 1024;  // ~98 KB incl. alignment slack: 2 CTAs per SM
 
 struct AttnParams {
   bf16* out;   // [B*N][E] bf16 (heads concatenated, like .transpose(1,2).reshape(B,N,C))
@@ -46,7 +49,7 @@ struct AttnParams {
   float scale_log2e;  // head_dim^-0.5 * log2(e)
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -82,25 +85,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t TM_S = tmem_base;         // S[b] at + b*128
-  const uint32_t TM_O = tmem_base + 256;   // O[b] at + b*64
+  const uint32_t TM_S = tmem_base;         // S[b] at + b*64
+  const uint32_t TM_O = tmem_base + 128;   // O[b] at + b*64
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_3d(smem + ATT_SMEM_Q, &tmQKV, q_full, head * ATT_D, q0, img);
+      tma_load_3d(smem + ATT_SMEM_Q + ATT_Q_BYTES / 2, &tmQKV, q_full, head * ATT_D, q0 + 64, img);
       uint32_t stage = 0, phase = 0;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
-        uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES;
-        uint8_t* sv = sk + ATT_TILE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES;
+        uint8_t* sv = sk + ATT_KV_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
         tma_load_3d(sk, &tmQKV, &kv_full[stage], p.E + head * ATT_D, j * ATT_BKV, img);
         tma_load_3d(sv, &tmQKV, &kv_full[stage], 2 * p.E + head * ATT_D, j * ATT_BKV, img);
         if (++stage == ATT_STAGES) { stage = 0; phase ^= 1u; }
@@ -109,7 +113,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, ATT_BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major: d contiguous)
       const uint32_t sq = smem_u32(smem + ATT_SMEM_Q);
       mbar_wait(q_full, 0);
@@ -120,11 +124,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
         mbar_wait(&p_full[b], it & 1u);  // P written (and O rescaled, if needed) by warpgroup b
         tc_fence_after();
-        const uint32_t sp = smem_u32(smem + ATT_SMEM_P + b * 2 * ATT_TILE_BYTES);
-        const uint32_t sv = smem_u32(smem + ATT_SMEM_KV + stage_i * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+        const uint32_t sp = smem_u32(smem + ATT_SMEM_P + b * ATT_P_BYTES);
+        const uint32_t sv = smem_u32(smem + ATT_SMEM_KV + stage_i * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t da = make_smem_desc_sw128(sp + kk * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 8192, 1024);
           umma_bf16(TM_O + b * 64, da, db, IDESC_O, (it > 0 || kk > 0) ? 1u : 0u);  // accumulate over this WG's tiles
         }
@@ -138,12 +142,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         mbar_wait(&kv_full[stage], phase);
         mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES);
+        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k) {
           const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
-          umma_bf16(TM_S + b * 128, da, db, IDESC_S, k > 0 ? 1u : 0u);
+          umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[b]);
         if (j > 0) issue_pv(j - 1);
@@ -157,7 +161,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const int quarter = warp & 3;    // TMEM lane quarter accessible to this warp
     const int r = quarter * 32 + lane;  // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    uint8_t* sp = smem + ATT_SMEM_P + wg * 2 * ATT_TILE_BYTES;
+    uint8_t* sp = smem + ATT_SMEM_P + wg * ATT_P_BYTES;
     float m_run = -INFINITY, l_run = 0.f;  // m_run: reference max the exponentials are taken against
     const float c = p.scale_log2e;
     const uint32_t to = TM_O + wg * 64 + lane_off;
@@ -167,11 +171,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       const int valid = p.N - j * ATT_BKV;  // number of real keys in this tile (>= 1)
       mbar_wait(&s_full[wg], it & 1u);
       tc_fence_after();
-      const uint32_t ts = TM_S + wg * 128 + lane_off;
+      const uint32_t ts = TM_S + wg * ATT_BKV + lane_off;
       // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < ATT_BKV / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(ts + ch * 32, v);
         tmem_ld_wait();
@@ -214,7 +218,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       // pass 2: p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem
       float rs = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < ATT_BKV / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(ts + ch * 32, v);
         tmem_ld_wait();
@@ -226,7 +230,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) e[t] = (ch * 32 + t < valid) ? ex2_approx(fmaf(__uint_as_float(v[t]), c, -mc)) : 0.f;
         }
-        uint8_t* blk = sp + (ch >> 1) * ATT_TILE_BYTES;
+        uint8_t* blk = sp;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 w;
@@ -234,7 +238,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
           w.y = pack_bf16x2(e[8 * g + 2], e[8 * g + 3]);
           w.z = pack_bf16x2(e[8 * g + 4], e[8 * g + 5]);
           w.w = pack_bf16x2(e[8 * g + 6], e[8 * g + 7]);
-          *reinterpret_cast<uint4*>(blk + sw128_offset(r, (ch & 1) * 4 + g)) = w;
+          *reinterpret_cast<uint4*>(blk + sw128_offset(r, ch * 4 + g)) = w;
 #pragma unroll
           for (int t = 0; t < 8; ++t) rs += e[8 * g + t];
         }
@@ -248,54 +252,50 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         mbar_arrive(&p_full[wg]);
       }
     }
-    // this warpgroup's O (sum over its KV tiles, relative to m_run) -> registers
-    float acc[ATT_D];
-    if (it > 0) {
-      mbar_wait(&o_full[wg], (it - 1u) & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(to + h * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) acc[h * 32 + t] = __uint_as_float(v[t]);
-      }
-    } else {
-#pragma unroll
-      for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
-    }
-
     // ---- combine the two warpgroups (split-KV merge) and write the output ----
-    float* xch = reinterpret_cast<float*>(smem + ATT_SMEM_P + 2 * ATT_TILE_BYTES);  // P[1] buffer: [64][128] floats
-    float* ml = reinterpret_cast<float*>(smem + ATT_SMEM_ML);                       // [2][128]
+    // Both O accumulators live in the SAME TMEM lanes (rows), 64 columns apart, so warpgroup 0 reads both
+    // straight out of TMEM; only m and l of warpgroup 1 travel through shared memory.
+    float* ml = reinterpret_cast<float*>(smem + ATT_SMEM_ML);  // [2][128]
     if (wg == 1) {
-#pragma unroll
-      for (int d = 0; d < ATT_D; ++d) xch[d * 128 + r] = acc[d];
       ml[r] = m_run;
       ml[128 + r] = l_run;
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 softmax warps only
     if (wg == 0) {
+      const uint32_t it1 = static_cast<uint32_t>(nkv / 2);  // tiles warpgroup 1 processed (it = tiles of WG0 >= 1)
+      mbar_wait(&o_full[0], (it - 1u) & 1u);
+      if (it1 > 0) mbar_wait(&o_full[1], (it1 - 1u) & 1u);
+      tc_fence_after();
       const float m1 = ml[r], l1 = ml[128 + r];
       const float m = fmaxf(m_run, m1);
-      const float a0 = exp2f((m_run - m) * c);
-      const float a1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - m) * c);
+      const float a0 = ex2_approx((m_run - m) * c);
+      const float a1 = (it1 == 0 || m1 == -INFINITY) ? 0.f : ex2_approx((m1 - m) * c);
       const float inv = 1.0f / (l_run * a0 + l1 * a1);
+      const float s0 = a0 * inv, s1 = a1 * inv;
       const int q = q0 + r;
-      if (q < p.N) {
-        bf16* o = p.out + (static_cast<size_t>(img) * p.N + q) * p.E + head * ATT_D;
+      bf16* o = p.out + (static_cast<size_t>(img) * p.N + q) * p.E + head * ATT_D;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(TM_O + lane_off + h * 32, v0);
+        tmem_ld32(TM_O + 64 + lane_off + h * 32, v1);  // never-written columns if it1 == 0: multiplied by s1 = 0
+        tmem_ld_wait();
+        if (q < p.N) {
 #pragma unroll
-        for (int g = 0; g < ATT_D / 8; ++g) {
-          float y[8];
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) y[t] = (acc[8 * g + t] * a0 + xch[(8 * g + t) * 128 + r] * a1) * inv;
-          uint4 w;
-          w.x = pack_bf16x2(y[0], y[1]);
-          w.y = pack_bf16x2(y[2], y[3]);
-          w.z = pack_bf16x2(y[4], y[5]);
-          w.w = pack_bf16x2(y[6], y[7]);
-          reinterpret_cast<uint4*>(o)[g] = w;
+            for (int t = 0; t < 8; ++t) {
+              const float b1 = (it1 > 0) ? __uint_as_float(v1[8 * g + t]) : 0.f;
+              y[t] = __uint_as_float(v0[8 * g + t]) * s0 + b1 * s1;
+            }
+            uint4 w;
+            w.x = pack_bf16x2(y[0], y[1]);
+            w.y = pack_bf16x2(y[2], y[3]);
+            w.z = pack_bf16x2(y[4], y[5]);
+            w.w = pack_bf16x2(y[6], y[7]);
+            reinterpret_cast<uint4*>(o)[h * 4 + g] = w;
+          }
         }
       }
     }
@@ -305,7 +305,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -323,7 +323,7 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
   CUtensorMap tm;
   uint64_t dims[3] = {(uint64_t)3 * E, (uint64_t)N, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)3 * E * 2, (uint64_t)N * 3 * E * 2};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, 64, 1};  // one 64-row box serves K, V (one load) and Q (two loads)
   int rc = make_tmap_bf16(&tm, qkv, 3, dims, str, box);
   if (rc != STEGO_OK) return rc;
   static bool configured = false;

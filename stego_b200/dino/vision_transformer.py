@@ -215,9 +215,38 @@ class VisionTransformer(nn.Module):
         return x, (qkv if want_qkv else None)
 
     @torch.no_grad()
-    def patch_features(self, img: torch.Tensor) -> torch.Tensor:
+    def patch_features(self, img: torch.Tensor, use_graph: bool = False) -> torch.Tensor:
         """norm(last block) with the cls token dropped, tokens-major bf16 [B, hw, E] — the tensor STEGO's
-        DinoFeaturizer builds at src/modules.py:97, in the K-major layout the correlation GEMM wants."""
+        DinoFeaturizer builds at src/modules.py:97, in the K-major layout the correlation GEMM wants.
+
+        use_graph=True replays the whole kernel sequence (~110 launches) as ONE CUDA graph captured per input
+        shape (the backbone is frozen and RNG-free).  The result then lives in a static buffer that the next
+        replay overwrites: only for callers that consume it before calling again (the fused training step)."""
+        if use_graph and img.is_cuda:
+            return self._graphed_patch_features(img)
+        return self._patch_features_eager(img)
+
+    def _graphed_patch_features(self, img: torch.Tensor) -> torch.Tensor:
+        from .. import _lib
+        self._prepared()
+        graphs = self._cache.setdefault("graphs", {})
+        key = (tuple(img.shape), img.device.index)
+        if key not in graphs:
+            self._patch_features_eager(img)  # warm-up: kernel attributes, pos-embed cache, allocator
+            torch.cuda.synchronize()
+            static_in = img.detach().float().contiguous().clone()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.load().stego_launch_count()
+            with torch.cuda.graph(g):
+                static_out = self._patch_features_eager(static_in)
+            graphs[key] = (g, static_in, static_out, _lib.load().stego_launch_count() - n0)
+        g, static_in, static_out, nlaunch = graphs[key]
+        static_in.copy_(img)
+        g.replay()
+        _lib.replayed_launches += nlaunch
+        return static_out
+
+    def _patch_features_eager(self, img: torch.Tensor) -> torch.Tensor:
         B = img.shape[0]
         x, _ = self.forward_tokens(img)
         w = self._prepared()

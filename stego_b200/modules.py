@@ -256,12 +256,13 @@ class DinoFeaturizer(nn.Module):
                                    torch.nn.Conv2d(in_channels, self.dim, (1, 1)))
 
     # ---- fused internals -------------------------------------------------------------------------
-    def backbone_tokens(self, img: torch.Tensor) -> torch.Tensor:
-        """Frozen ViT -> bf16 tokens-major features [B, hw, E] (cls dropped)."""
+    def backbone_tokens(self, img: torch.Tensor, use_graph: bool = False) -> torch.Tensor:
+        """Frozen ViT -> bf16 tokens-major features [B, hw, E] (cls dropped).  use_graph: replay the kernel
+        sequence as one CUDA graph (result is a static buffer valid until the next call)."""
         self.model.eval()
         assert img.shape[2] % self.patch_size == 0
         assert img.shape[3] % self.patch_size == 0
-        return self.model.patch_features(img)
+        return self.model.patch_features(img, use_graph=use_graph)
 
     def draw_masks(self, batch: int, device):
         """Dropout2d noises in the reference's call order: cluster1 input, cluster2 input, returned feats."""

@@ -234,7 +234,8 @@ class LitUnsupervisedSegmenter(nn.Module):
 
         # frozen backbone on img ++ img_pos in one pass (reference: two net() calls, :130,:132)
         with torch.no_grad():
-            tok_all = net.backbone_tokens(torch.cat([img, img_pos], 0) if use_pos else img)  # [2B, hw, E] bf16
+            tok_all = net.backbone_tokens(torch.cat([img, img_pos], 0) if use_pos else img,
+                                          use_graph=getattr(cfg, "cuda_graph", True))  # [2B, hw, E] bf16
         # Dropout2d noises in the reference's RNG order: net(img) draws three, then net(img_pos) draws three
         m1, m2, m3 = net.draw_masks(B, img.device)
         if use_pos:
