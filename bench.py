@@ -333,23 +333,55 @@ def main():
     batch = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     loss_host = torch.zeros(1).pin_memory()
+    loss_ring = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def stage_batch():
+        """H2D copy of one step's inputs from pinned host memory on a side stream (overlaps the previous step)."""
+        with torch.cuda.stream(copy_stream):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return b, ev
+
     def run(nsteps, e2e):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for i in range(nsteps):
-            if e2e:
-                b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        if e2e:
+            # every step: inputs come from pinned host memory (H2D inside the timed region, prefetched one step
+            # ahead on a copy stream like a pin_memory DataLoader) and the step's loss is read back to the host
+            # (D2H, one step delayed so the host never stalls the launch queue).
+            pending = []
+            nxt = stage_batch()
+            for i in range(nsteps):
+                b, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                for t in b.values():
+                    t.record_stream(torch.cuda.current_stream())
+                if i + 1 < nsteps:
+                    nxt = stage_batch()
                 loss = model.training_step(b, i)
-                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-                torch.cuda.current_stream().synchronize()  # the user reads the loss every step
-            else:
+                slot = loss_ring[i % 2]
+                slot.copy_(loss.detach().reshape(1), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                pending.append((done, slot))
+                if len(pending) > 1:
+                    d0, s0 = pending.pop(0)
+                    d0.synchronize()
+                    loss_host.copy_(s0)  # the host really reads the value
+            for d0, s0 in pending:
+                d0.synchronize()
+                loss_host.copy_(s0)
+        else:
+            for i in range(nsteps):
                 model.training_step(batch, i)
         e.record()
         barrier()

@@ -87,12 +87,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // host) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  // try_wait suspends the thread for a hardware time slice by itself; keep the retry loop to two instructions and
+  // consult the (expensive) global timer only every 64K retries.
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > STEGO_MBAR_TIMEOUT_NS) {
-      printf("stego_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 0xFFFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > STEGO_MBAR_TIMEOUT_NS) {
+        printf("stego_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -280,6 +280,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = half; c < BN / 32; c += 2) {
             const int col0 = tn * BN + c * 32;
             if (col0 >= p.N) break;
+            const int col = col0 + chunk * 4;
+            // all residual loads first (out may alias residual: the compiler cannot hoist loads over the stores,
+            // so issuing them together is what keeps 8 x 512 B per warp in flight instead of one)
+            float4 rr[8];
+            if (p.residual != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int grow = row_base + i * 4 + rsub;
+                rr[i] = (grow < p.M && col < p.N)
+                            ? *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
@@ -305,17 +321,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<float4*>(buf + sw128_offset(lane, j)) =
                   make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             __syncwarp();
-            const int col = col0 + chunk * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + rsub;
               const int grow = row_base + r;
               if (grow < p.M && col < p.N) {
                 float4 y = *reinterpret_cast<const float4*>(buf + sw128_offset(r, chunk));
-                if (p.residual != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col);
-                  y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
-                }
+                y.x += rr[i].x; y.y += rr[i].y; y.z += rr[i].z; y.w += rr[i].w;
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + col) = y;
               }
             }

@@ -244,75 +244,69 @@ linear_ce_kernel(LinearCEParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // lanes = classes: lane k owns logit k of the pixel the warp is working on; the warp walks its rows pixel by
+  // pixel, softmax statistics are two warp reductions, and the gradient of the 4 low-res taps is kept in four
+  // per-lane registers that are flushed to the shared box only when the tap set changes (every H/h pixels).
+  const bool kact = lane < p.n;
   float lsum = 0.f, cnt = 0.f;
   for (int row = warp; row < LCE_TILE; row += 8) {
-    const int Y = Y0 + row, X = X0 + lane;
-    const bool inb = (Y < p.H) && (X < p.W);
-    long long lab = -1;
-    if (inb) lab = p.label[(1ll * b * p.H + Y) * p.W + X];
-    const bool valid = inb && lab >= 0 && lab < p.n;
-    int y0, y1, x0, x1;
-    float ly, lx;
-    src_index(min(Y, p.H - 1), sy, p.h, y0, y1, ly);
-    src_index(min(X, p.W - 1), sx, p.w, x0, x1, lx);
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const int c00 = ((y0 - by0) * bw + (x0 - bx0)) * LP_LD, c01 = ((y0 - by0) * bw + (x1 - bx0)) * LP_LD;
-    const int c10 = ((y1 - by0) * bw + (x0 - bx0)) * LP_LD, c11 = ((y1 - by0) * bw + (x1 - bx0)) * LP_LD;
-    float z[LP_LD];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < LP_LD; ++k) {
-      if (k < p.n) {
-        z[k] = w00 * slog[c00 + k] + w01 * slog[c01 + k] + w10 * slog[c10 + k] + w11 * slog[c11 + k];
-        mx = fmaxf(mx, z[k]);
-      }
-    }
-    float se = 0.f;
-#pragma unroll
-    for (int k = 0; k < LP_LD; ++k)
-      if (k < p.n) se += expf(z[k] - mx);
-    const float lse = mx + logf(se);
-    if (valid) {
-      float zl = 0.f;
-#pragma unroll
-      for (int k = 0; k < LP_LD; ++k)
-        if (k == lab) zl = z[k];
-      lsum += lse - zl;
-      cnt += 1.f;
-    }
-    if (p.dlogits) {
-      // lanes with identical (x0, x1) form contiguous runs (x is monotone in the lane index)
-      const int key = x0 * 2 + (x1 - x0);
-      const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-      const bool leader = (lane == 0) || (key_prev != key);
-      bool same[5];
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const int d = 1 << s;
-        const int kd = __shfl_down_sync(0xffffffffu, key, d);
-        same[s] = (lane + d < 32) && (kd == key);
-      }
-#pragma unroll
-      for (int k = 0; k < LP_LD; ++k) {
-        if (k < p.n) {
-          const float g = valid ? (expf(z[k] - lse) - ((k == lab) ? 1.f : 0.f)) : 0.f;
-          float v0 = g * (1.f - lx), v1 = g * lx;  // x-weights; y-weights applied by the leader
-#pragma unroll
-          for (int s = 0; s < 5; ++s) {
-            const float a0 = __shfl_down_sync(0xffffffffu, v0, 1 << s);
-            const float a1 = __shfl_down_sync(0xffffffffu, v1, 1 << s);
-            if (same[s]) { v0 += a0; v1 += a1; }
-          }
-          if (leader && (v0 != 0.f || v1 != 0.f)) {
-            atomicAdd(&sgrad[c00 + k], v0 * (1.f - ly));
-            atomicAdd(&sgrad[c01 + k], v1 * (1.f - ly));
-            atomicAdd(&sgrad[c10 + k], v0 * ly);
-            atomicAdd(&sgrad[c11 + k], v1 * ly);
-          }
+    const int Y = Y0 + row;
+    if (Y >= p.H) break;
+    int y0, y1;
+    float ly;
+    src_index(Y, sy, p.h, y0, y1, ly);
+    const int r0 = (y0 - by0) * bw, r1 = (y1 - by0) * bw;
+    int cur00 = -1, cur11 = -1, cur01 = 0, cur10 = 0;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    const long long* lrow = p.label + (1ll * b * p.H + Y) * p.W;
+    for (int px = 0; px < LCE_TILE; ++px) {
+      const int X = X0 + px;
+      if (X >= p.W) break;
+      const long long lab = lrow[X];  // same address in every lane: one broadcast transaction
+      const bool valid = lab >= 0 && lab < p.n;
+      int x0, x1;
+      float lx;
+      src_index(X, sx, p.w, x0, x1, lx);
+      const int c00 = (r0 + x0 - bx0) * LP_LD, c01 = (r0 + x1 - bx0) * LP_LD;
+      const int c10 = (r1 + x0 - bx0) * LP_LD, c11 = (r1 + x1 - bx0) * LP_LD;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      if (p.dlogits && (c00 != cur00 || c11 != cur11)) {
+        if (cur00 >= 0 && kact) {
+          atomicAdd(&sgrad[cur00 + lane], a00);
+          atomicAdd(&sgrad[cur01 + lane], a01);
+          atomicAdd(&sgrad[cur10 + lane], a10);
+          atomicAdd(&sgrad[cur11 + lane], a11);
         }
+        cur00 = c00; cur01 = c01; cur10 = c10; cur11 = c11;
+        a00 = a01 = a10 = a11 = 0.f;
       }
+      if (!valid) continue;  // warp-uniform
+      const float z = kact ? (w00 * slog[c00 + lane] + w01 * slog[c01 + lane] + w10 * slog[c10 + lane] +
+                              w11 * slog[c11 + lane])
+                           : -INFINITY;
+      const float mx = warp_max(z);
+      const float e = kact ? expf(z - mx) : 0.f;
+      const float se = warp_sum(e);
+      const float zl = __shfl_sync(0xffffffffu, z, static_cast<int>(lab));
+      lsum += (mx + logf(se)) - zl;  // identical in every lane; lane 0's copy is used
+      cnt += 1.f;
+      if (p.dlogits) {
+        const float g = e / se - ((lane == lab) ? 1.f : 0.f);
+        a00 = fmaf(g, w00, a00);
+        a01 = fmaf(g, w01, a01);
+        a10 = fmaf(g, w10, a10);
+        a11 = fmaf(g, w11, a11);
+      }
+    }
+    if (p.dlogits && cur00 >= 0 && kact) {
+      atomicAdd(&sgrad[cur00 + lane], a00);
+      atomicAdd(&sgrad[cur01 + lane], a01);
+      atomicAdd(&sgrad[cur10 + lane], a10);
+      atomicAdd(&sgrad[cur11 + lane], a11);
     }
   }
+  // every lane carries the same lsum / cnt: keep lane 0's
+  if (lane != 0) { lsum = 0.f; cnt = 0.f; }
   lsum = warp_sum(lsum);
   cnt = warp_sum(cnt);
   if (lane == 0) { sred[0][warp] = lsum; sred[1][warp] = cnt; }
