@@ -286,6 +286,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also report per-phase device time of the step")
     args = ap.parse_args()
     cfgd = dict(CONFIGS[args.config])
     if args.batch:
@@ -400,6 +401,15 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)
     ms_e2e = run(args.steps, True)
+    phases = None
+    if args.breakdown:
+        model.profile_marks = []
+        run(args.steps, False)
+        marks, model.profile_marks = model.profile_marks, None
+        phases = {}
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            if n1 != "start":
+                phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
     loss_val = float(loss_host.item())
 
     if rank != 0:
@@ -422,6 +432,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "last_loss": loss_val,
+        **({"phase_ms": {k: round(v, 4) for k, v in phases.items()}} if phases else {}),
         "step_tensor_roofline": {"flops_per_image": fl_img, "achieved_tflops": value / world * fl_img / 1e12,
                                  "peak_tflops_sustained": peaks["tf_sust"],
                                  "frac": value / world * fl_img / 1e12 / peaks["tf_sust"], "peak_source": peaks["source"]},

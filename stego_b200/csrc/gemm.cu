@@ -37,6 +37,7 @@ struct GemmParams {
   int atomic;         // 1: fp32 atomicAdd into out (split-K)
   int vec_ok;         // host-verified 16-byte alignment of out/residual rows
   int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
+  int tma_epi;        // 1: epilogue tiles leave through TMA stores; 2: TMA fp32 reduce-add (in-place residual)
 };
 
 // Exact (erf) GELU, nn.GELU default.  erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one rcp + one ex2 on
@@ -75,7 +76,8 @@ __device__ __forceinline__ float gelu_erf_poly(float x) {
 
 template <int BN, int kStages, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, GemmParams p) {
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -85,7 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr uint32_t EPI_BYTES = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
+  constexpr uint32_t EPI_BYTES = 8 * 2 * 4096;  // two 32-row x 128-byte staging tiles per epilogue warp
   uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
@@ -104,6 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epi) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -192,10 +195,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;        // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate column groups
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t epi_groups = 0;  // bulk-store groups this warp has committed (selects the staging tile)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tn = (t / p.splits) % tiles_n;
       const int tm = t / (p.splits * tiles_n);
-      if (p.fast_epi && p.residual != nullptr) {
+      if (p.fast_epi && !p.tma_epi && p.residual != nullptr) {
         // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
         const int prow = tm * GEMM_BM + quarter * 32 + lane;
         if (prow < p.M) {
@@ -216,6 +220,111 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         res_row = row % p.row_div + 1;
       }
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (p.tma_epi) {
+        // ---- TMA epilogue: TMEM -> regs (bias/act) -> swizzled smem staging tile -> ONE bulk tensor store (or fp32
+        //      reduce-add for the in-place residual update x += ...) per 32 x 128-byte tile.  No global load/store
+        //      instructions, edges clipped by the tensor map, staging double-buffered per warp.
+        uint8_t* buf0 = epi_smem + (warp - 2) * 8192;
+        const int row_base = tm * GEMM_BM + quarter * 32;
+        if (p.out_bf16) {
+#pragma unroll 1
+          for (int c = half; c < BN / 64; c += 2) {
+            const int col0 = tn * BN + c * 64;
+            if (col0 >= p.N) break;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + c * 64, v0);
+            tmem_ld32(taddr + c * 64 + 32, v1);
+            uint8_t* buf = buf0 + (epi_groups & 1u) * 4096;
+            if (lane == 0) tma_wait_group_read<1>();  // the store that last read this staging tile is done with it
+            __syncwarp();
+            tmem_ld_wait();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t* v = hh ? v1 : v0;
+              const int cb = col0 + hh * 32;
+              float x[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+              if (p.bias != nullptr && cb < p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
+                  x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                }
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = gelu_erf_poly(x[j]);
+              } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+                w.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+                w.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+                w.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+                *reinterpret_cast<uint4*>(buf + sw128_offset(lane, hh * 4 + j)) = w;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(buf, &tmO, col0, row_base);
+              tma_commit_group();
+            }
+            ++epi_groups;
+          }
+        } else {
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += 2) {
+            const int col0 = tn * BN + c * 32;
+            if (col0 >= p.N) break;
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            uint8_t* buf = buf0 + (epi_groups & 1u) * 4096;
+            if (lane == 0) tma_wait_group_read<1>();
+            __syncwarp();
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + sw128_offset(lane, j)) =
+                  make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.tma_epi == 2) tma_reduce_add_2d(buf, &tmO, col0, row_base);
+              else tma_store_2d(buf, &tmO, col0, row_base);
+              tma_commit_group();
+            }
+            ++epi_groups;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       if (p.fast_epi) {
         // ---- coalesced epilogue: TMEM -> regs (bias/act) -> per-warp swizzled smem transpose -> 128-byte row
         //      segments: every global load/store instruction covers 4 full rows x 128 B.
@@ -418,6 +527,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if (p.tma_epi && warp >= 2 && lane == 0) tma_wait_group_read<0>();  // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -427,8 +537,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, int kStages, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * 4096 + 1024 + 256;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+                       cudaStream_t stream) {
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * 2 * 4096 + 1024 + 256;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
@@ -438,7 +549,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p);
   STEGO_CHECK_LAUNCH("gemm_bf16_kernel launch");
   return STEGO_OK;
 }
@@ -482,7 +593,15 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
   const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
 
-  CUtensorMap tmA, tmB;
+  // TMA epilogue: plain store for outputs without a residual; fp32 reduce-add when the residual IS the output
+  // (the in-place x += ... of the transformer blocks) — then the epilogue issues no global loads at all.
+  p.tma_epi = 0;
+  if (p.fast_epi && !b_mn_major && !a_mn_major) {
+    if (residual == nullptr) p.tma_epi = 1;
+    else if (!out_bf16 && residual == out && ldr == ldo) p.tma_epi = 2;
+  }
+
+  CUtensorMap tmA, tmB, tmO;
   int rc;
   {
     // K-major: tensor is [M][K] (inner = K). MN-major: tensor is [K][M] (inner = M).
@@ -497,9 +616,18 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     uint32_t box[2] = {64, b_mn_major ? 64u : (wide ? 256u : 128u)};
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
-  if (wide) return launch_gemm<256, 4, false, false>(tmA, tmB, p, stream);
-  if (!a_mn_major && !b_mn_major) return launch_gemm<128, 6, false, false>(tmA, tmB, p, stream);
-  if (!a_mn_major && b_mn_major) return launch_gemm<128, 6, false, true>(tmA, tmB, p, stream);
-  if (a_mn_major && b_mn_major) return launch_gemm<128, 6, true, true>(tmA, tmB, p, stream);
-  return launch_gemm<128, 6, true, false>(tmA, tmB, p, stream);
+  if (p.tma_epi) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)ldo * esz};
+    uint32_t box[2] = {out_bf16 ? 64u : 32u, 32u};
+    rc = out_bf16 ? make_tmap_bf16(&tmO, out, 2, dims, str, box) : make_tmap_f32(&tmO, out, 2, dims, str, box);
+    if (rc != STEGO_OK) return rc;
+  } else {
+    tmO = tmA;  // unused
+  }
+  if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
+  if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
+  if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);
+  if (a_mn_major && b_mn_major) return launch_gemm<128, 5, true, true>(tmA, tmB, tmO, p, stream);
+  return launch_gemm<128, 5, true, false>(tmA, tmB, tmO, p, stream);
 }

@@ -77,22 +77,38 @@ relu_bwd_kernel(const float* __restrict__ dh, const bf16* __restrict__ h, bf16* 
   reinterpret_cast<uint2*>(out)[idx] = w;
 }
 
-// out[c] += sum over rows of in[row][c]; one thread per column, row-chunk per blockIdx.y
-template <typename T>
-__global__ void __launch_bounds__(128)
-colsum_kernel(const T* __restrict__ in, int ld, int C, long long rows, int rows_per_block, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const long long r0 = 1ll * blockIdx.y * rows_per_block;
-  const long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
-  float acc = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    if constexpr (sizeof(T) == 2)
-      acc += __bfloat162float(in[r * ld + c]);
-    else
-      acc += in[r * ld + c];
+// out[c] += sum over rows of in[row][c].  One warp per 32-row chunk, lanes stride over the columns (coalesced
+// row reads), block-level combine in shared memory, one atomic per (block, column).
+template <typename T, int NV>  // NV = ceil(C / 32)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ in, int ld, int C, long long rows, float* __restrict__ out) {
+  __shared__ float part[8][NV * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (1ll * blockIdx.x * 8 + warp) * 32;
+  float acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+  for (long long r = r0; r < r0 + 32 && r < rows; ++r) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) {
+        if constexpr (sizeof(T) == 2)
+          acc[k] += __bfloat162float(in[r * ld + c]);
+        else
+          acc[k] += in[r * ld + c];
+      }
+    }
   }
-  atomicAdd(out + c, acc);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) part[warp][lane + 32 * k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][c];
+    atomicAdd(out + c, t);
+  }
 }
 
 // torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False): step is 1-based.
@@ -154,12 +170,17 @@ extern "C" int stego_relu_bwd_bf16(const float* dh, const void* h_bf16, void* ou
 extern "C" int stego_colsum(const void* in, int in_is_bf16, int ld, int C, long long rows, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(in && out && C > 0 && C <= ld && rows > 0, "stego_colsum: bad args");
-  const int rpb = 512;
-  dim3 grid((C + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-  if (in_is_bf16)
-    colsum_kernel<bf16><<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(in), ld, C, rows, rpb, out);
-  else
-    colsum_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(in), ld, C, rows, rpb, out);
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  const int nv = (C + 31) / 32;
+#define STEGO_COLSUM(T, NV) colsum_kernel<T, NV><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(in), ld, C, rows, out)
+  if (in_is_bf16) {
+    if (nv <= 3) STEGO_COLSUM(bf16, 3); else if (nv <= 12) STEGO_COLSUM(bf16, 12); else if (nv <= 24) STEGO_COLSUM(bf16, 24);
+    else { set_error("stego_colsum: C=%d unsupported (<= 768)", C); return STEGO_ERR_UNSUPPORTED; }
+  } else {
+    if (nv <= 3) STEGO_COLSUM(float, 3); else if (nv <= 12) STEGO_COLSUM(float, 12); else if (nv <= 24) STEGO_COLSUM(float, 24);
+    else { set_error("stego_colsum: C=%d unsupported (<= 768)", C); return STEGO_ERR_UNSUPPORTED; }
+  }
+#undef STEGO_COLSUM
   STEGO_CHECK_LAUNCH("colsum_kernel");
   return STEGO_OK;
 }

@@ -195,6 +195,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         self.logged: Dict[str, torch.Tensor] = {}
         self._flat: Optional[FlatParams] = None
         self._spec = corr.LossSpec(cfg)
+        self.profile_marks = None  # optional list: bench.py --breakdown collects (name, cuda event) pairs here
 
     # ---- Lightning-shaped surface ----------------------------------------------------------------
     def forward(self, x):
@@ -218,6 +219,12 @@ class LitUnsupervisedSegmenter(nn.Module):
             self.configure_optimizers()
         return tuple(self._flat.optimizers)
 
+    def _mark(self, name):
+        if self.profile_marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile_marks.append((name, ev))
+
     # ---- the step ---------------------------------------------------------------------------------
     def training_step(self, batch, batch_idx):
         cfg = self.cfg
@@ -226,6 +233,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         linear_probe_optim.zero_grad()
         cluster_probe_optim.zero_grad()
 
+        self._mark("start")
         img, img_pos, label = batch["img"], batch["img_pos"], batch["label"]
         B = img.shape[0]
         net = self.net
@@ -236,6 +244,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         with torch.no_grad():
             tok_all = net.backbone_tokens(torch.cat([img, img_pos], 0) if use_pos else img,
                                           use_graph=getattr(cfg, "cuda_graph", True))  # [2B, hw, E] bf16
+        self._mark("vit_forward")
         # Dropout2d noises in the reference's RNG order: net(img) draws three, then net(img_pos) draws three
         m1, m2, m3 = net.draw_masks(B, img.device)
         if use_pos:
@@ -249,6 +258,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         E = tok_all.shape[-1]
         feats = tok_all[:B].view(B, fh, fw, E).permute(0, 3, 1, 2)  # NCHW view, bf16, channel stride 1
 
+        self._mark("head_forward")
         loss = 0
         if use_pos:
             code_pos = code_all[B:]
@@ -296,6 +306,7 @@ class LitUnsupervisedSegmenter(nn.Module):
                 self.log('loss/crf', crf)
                 loss = loss + cfg.crf_weight * crf
 
+        self._mark("corr_loss_forward")
         detached_code = code.detach()
         linear_loss = linear_probe_ce(detached_code, self.linear_probe.weight, self.linear_probe.bias, label)
         loss = loss + linear_loss
@@ -305,12 +316,15 @@ class LitUnsupervisedSegmenter(nn.Module):
         self.log('loss/cluster', cluster_loss)
         self.log('loss/total', loss)
 
+        self._mark("probes_forward")
         loss.backward()  # manual_backward (:227)
         self._flat.rebind()
+        self._mark("backward")
         allreduce_gradients(self._flat)
         net_optim.step()
         cluster_probe_optim.step()
         linear_probe_optim.step()
+        self._mark("allreduce_adam")
 
         if cfg.reset_probe_steps is not None and self.global_step == cfg.reset_probe_steps:
             raise RuntimeError("stego_b200: reset_probe_steps is not supported on the flat-buffer optimiser yet")
