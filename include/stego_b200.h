@@ -139,7 +139,7 @@ STEGO_API int stego_adam_step(float* param, const float* grad, float* exp_avg, f
 /* ClusterLookup.forward (src/modules.py:146-161). x has element strides (batch, channel, pixel) with
  * pixel = y*W + x; clusters [n][C].  use_alpha = 0 is `alpha is None` (one-hot argmax).
  * loss_out[0] = -(probs * inner_products).sum(1).mean().  Optional outputs (may be null): assign [B][npix]
- * int64 argmax, probs [B][n][npix], log_probs [B][n][npix] (needs alpha).  scratch: >= 8*SMs floats. */
+ * int64 argmax, probs [B][n][npix], log_probs [B][n][npix] (needs alpha).  scratch: >= 16*SMs floats. */
 STEGO_API int stego_cluster_lookup_fwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
                                        const float* clusters, int B, int C, int n_classes, long long npix,
                                        int use_alpha, float alpha, long long* assign, float* probs, float* log_probs,

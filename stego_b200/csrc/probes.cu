@@ -133,6 +133,105 @@ cluster_lookup_kernel(ClusterParams p) {
   }
 }
 
+// Channels-last variant (channel stride 1; the layout of the training step): one WARP per pixel, lanes = classes.
+// The pixel's channels sit in 3 registers per lane and are broadcast with shuffles; each lane accumulates the dot
+// product with "its" centroid in the same ascending-channel FMA order as the per-thread kernel above, so both
+// kernels produce identical inner products.  Handles alpha=None forward/backward and the softmax forward.
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+cluster_lookup_cl_kernel(ClusterParams p) {
+  extern __shared__ float sm[];
+  float* sncT = sm;                        // [C][32] transposed normalised centroids (lanes >= n read 0)
+  float* sacc = sm + p.C * 32;             // backward: [n][C]
+  __shared__ float sred[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.C * 32; i += blockDim.x) sncT[i] = 0.f;
+  if (kBackward)
+    for (int i = threadIdx.x; i < p.n * p.C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  for (int k = warp; k < p.n; k += 8) {
+    float ss = 0.f;
+    for (int c = lane; c < p.C; c += 32) { const float v = p.clusters[k * p.C + c]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < p.C; c += 32) sncT[c * 32 + k] = p.clusters[k * p.C + c] * inv;
+  }
+  __syncthreads();
+  const float gs = kBackward ? p.grad_scale * p.grad_loss[0] : 0.f;
+  const long long total = 1ll * p.B * p.npix;
+  float loss_acc = 0.f;
+  for (long long pix = 1ll * blockIdx.x * 8 + warp; pix < total; pix += 1ll * gridDim.x * 8) {
+    const int b = static_cast<int>(pix / p.npix);
+    const long long q = pix % p.npix;
+    const float* xp = p.x + b * p.sb + q * p.sp;
+    float xr[3];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      xr[k] = (c < p.C) ? xp[c] : 0.f;
+    }
+    // same summation order as the per-thread kernel is not required for the norm (it only scales all classes)
+    ss = warp_sum(xr[0] * xr[0] + xr[1] * xr[1] + xr[2] * xr[2]);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int c = 32 * k + j;
+        if (c < p.C) {  // warp-uniform
+          const float xc = __shfl_sync(0xffffffffu, xr[k], j);
+          d = fmaf(xc * inv, sncT[c * 32 + lane], d);
+        }
+      }
+    }
+    const float ip = (lane < p.n) ? d : -INFINITY;
+    const float best = warp_max(ip);
+    const int arg = __ffs(__ballot_sync(0xffffffffu, ip == best)) - 1;  // first maximum, like torch.argmax
+    if (p.mode == 0) {
+      if (lane == 0) loss_acc += best;
+      if (!kBackward) {
+        if (p.assign && lane == 0) p.assign[pix] = arg;
+        if (p.probs && lane < p.n) p.probs[(1ll * b * p.n + lane) * p.npix + q] = (lane == arg) ? 1.f : 0.f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int c = lane + 32 * k;
+          if (c < p.C) atomicAdd(&sacc[arg * p.C + c], gs * xr[k] * inv);
+        }
+      }
+    } else {
+      const float sc = ip * p.alpha;
+      const float mx = warp_max(lane < p.n ? sc : -INFINITY);
+      const float e = (lane < p.n) ? expf(sc - mx) : 0.f;
+      const float lse = mx + logf(warp_sum(e));
+      const float lp = sc - lse;
+      const float pk = (lane < p.n) ? expf(lp) : 0.f;
+      const float dotp = warp_sum((lane < p.n) ? pk * ip : 0.f);
+      if (lane == 0) loss_acc += dotp;
+      if (p.assign && lane == 0) p.assign[pix] = arg;
+      if (lane < p.n) {
+        if (p.probs) p.probs[(1ll * b * p.n + lane) * p.npix + q] = pk;
+        if (p.logp) p.logp[(1ll * b * p.n + lane) * p.npix + q] = lp;
+      }
+    }
+  }
+  if (!kBackward) {
+    if (lane == 0) sred[warp] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sred[w];
+      p.loss_partials[blockIdx.x] = t;
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n * p.C; i += blockDim.x)
+      if (sacc[i] != 0.f) atomicAdd(p.dnc + i, sacc[i]);
+  }
+}
+
 // d clusters from d normalised clusters: row-wise normalize backward
 __global__ void cluster_norm_bwd_kernel(const float* __restrict__ clusters, const float* __restrict__ dnc,
                                         float* __restrict__ dclusters, int n, int C) {
@@ -170,21 +269,35 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int n, f
 // ---------------------------------------------------------------------------------------------
 constexpr int LP_LD = 32;  // row stride of the low-res logit / grad buffers (n_classes <= 32)
 
-__global__ void __launch_bounds__(128)
+// one warp per low-res pixel, lanes = classes: channels are broadcast with shuffles, W^T sits in smem as [C][32]
+__global__ void __launch_bounds__(256)
 linear_logits_kernel(const float* __restrict__ code, long long ld_code, int C, const float* __restrict__ W,
                      const float* __restrict__ bias, int n, float* __restrict__ logits, long long rows) {
-  extern __shared__ float sw[];  // [n][C] + [n]
-  for (int i = threadIdx.x; i < n * C; i += blockDim.x) sw[i] = W[i];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sw[n * C + i] = bias[i];
+  extern __shared__ float sw[];  // [C][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i >> 5, k = i & 31;
+    sw[i] = (k < n) ? W[k * C + c] : 0.f;
+  }
   __syncthreads();
-  const long long r = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float xv[PR_MAX_DIM];
-  for (int c = 0; c < C; ++c) xv[c] = code[r * ld_code + c];
-  for (int k = 0; k < n; ++k) {
-    float d = sw[n * C + k];
-    for (int c = 0; c < C; ++c) d = fmaf(xv[c], sw[k * C + c], d);
-    logits[r * LP_LD + k] = d;
+  const float bk = (lane < n) ? bias[lane] : 0.f;
+  for (long long r = 1ll * blockIdx.x * 8 + warp; r < rows; r += 1ll * gridDim.x * 8) {
+    float xr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      xr[k] = (c < C) ? code[r * ld_code + c] : 0.f;
+    }
+    float d = bk;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int c = 32 * k + j;
+        if (c < C) d = fmaf(__shfl_sync(0xffffffffu, xr[k], j), sw[c * 32 + lane], d);
+      }
+    }
+    logits[r * LP_LD + lane] = (lane < n) ? d : 0.f;
   }
 }
 
@@ -335,23 +448,40 @@ __global__ void linear_ce_finish_kernel(const double* __restrict__ acc, float* _
 }
 
 // dW[k][c] += (gscale/count) * sum_r dlogits[r][k] code[r][c];  db[k] += (gscale/count) * sum_r dlogits[r][k]
-__global__ void __launch_bounds__(128)
+// One CTA per 128-row chunk: both operand tiles are staged in shared memory, every thread owns ~8 of the
+// n*C outputs and walks the 128 rows; one atomic per (CTA, output).
+constexpr int LW_ROWS = 128;
+__global__ void __launch_bounds__(256)
 linear_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ code, long long ld_code, int C, int n,
-                    long long rows, int rows_per_block, const float* __restrict__ loss_out, float gscale,
-                    float* __restrict__ dW, float* __restrict__ db) {
-  const int k = blockIdx.x;
-  const long long r0 = 1ll * blockIdx.y * rows_per_block;
-  const long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
-  const int c = threadIdx.x;
-  const float s = gscale / loss_out[1];
-  float acc = 0.f, accb = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const float g = dlogits[r * LP_LD + k];
-    if (c < C) acc = fmaf(g, code[r * ld_code + c], acc);
-    accb += g;
+                    long long rows, const float* __restrict__ loss_out, float gscale, float* __restrict__ dW,
+                    float* __restrict__ db) {
+  extern __shared__ float sm[];
+  float* sdl = sm;                    // [128][32]
+  float* scode = sm + LW_ROWS * 32;   // [128][C]
+  const long long r0 = 1ll * blockIdx.x * LW_ROWS;
+  const int nr = static_cast<int>((rows - r0 < LW_ROWS) ? rows - r0 : LW_ROWS);
+  for (int i = threadIdx.x; i < LW_ROWS * 32; i += blockDim.x) {
+    const int r = i >> 5;
+    sdl[i] = (r < nr) ? dlogits[(r0 + r) * LP_LD + (i & 31)] : 0.f;
   }
-  if (c < C) atomicAdd(dW + k * C + c, acc * s);
-  if (c == 0) atomicAdd(db + k, accb * s);
+  for (int i = threadIdx.x; i < LW_ROWS * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    scode[i] = (r < nr) ? code[(r0 + r) * ld_code + c] : 0.f;
+  }
+  __syncthreads();
+  const float s = gscale / loss_out[1];
+  for (int o = threadIdx.x; o < n * C; o += blockDim.x) {
+    const int k = o / C, c = o % C;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < LW_ROWS; ++r) acc = fmaf(sdl[r * 32 + k], scode[r * C + c], acc);
+    atomicAdd(dW + o, acc * s);
+  }
+  if (threadIdx.x < n) {
+    float acc = 0.f;
+    for (int r = 0; r < LW_ROWS; ++r) acc += sdl[r * 32 + threadIdx.x];
+    atomicAdd(db + threadIdx.x, acc * s);
+  }
 }
 
 }  // namespace stego
@@ -377,7 +507,7 @@ static int cluster_grid(long long total) {
 }
 
 // x: features with element strides (batch, channel, pixel); pixel index = y*W + x must be a single stride.
-// loss_out[0] = -(sum_k probs_k ip_k).mean(); scratch: at least 8*SMs floats.
+// loss_out[0] = -(sum_k probs_k ip_k).mean(); scratch: at least 16*SMs floats.
 extern "C" int stego_cluster_lookup_fwd(const float* x, long long stride_b, long long stride_c, long long stride_pix,
                                         const float* clusters, int B, int C, int n_classes, long long npix,
                                         int use_alpha, float alpha, long long* assign, float* probs, float* log_probs,
@@ -390,10 +520,19 @@ extern "C" int stego_cluster_lookup_fwd(const float* x, long long stride_b, long
   STEGO_CHECK_ARG(!log_probs || use_alpha, "stego_cluster_lookup_fwd: log_probs needs alpha");
   p.assign = assign; p.probs = probs; p.logp = log_probs; p.loss_partials = scratch;
   const long long total = 1ll * B * npix;
-  const int grid = cluster_grid(total);
-  const size_t smem = (size_t)(n_classes * C + 8) * sizeof(float);
-  cluster_lookup_kernel<false><<<grid, PR_THREADS, smem, stream>>>(p);
-  STEGO_CHECK_LAUNCH("cluster_lookup_kernel<fwd>");
+  int grid;
+  if (stride_c == 1 && n_classes <= 32) {
+    long long g = (total + 7) / 8;
+    const long long cap = 16ll * num_sms();
+    grid = (int)(g < cap ? g : cap);
+    cluster_lookup_cl_kernel<false><<<grid, 256, (size_t)C * 32 * sizeof(float), stream>>>(p);
+    STEGO_CHECK_LAUNCH("cluster_lookup_cl_kernel<fwd>");
+  } else {
+    grid = cluster_grid(total);
+    const size_t smem = (size_t)(n_classes * C + 8) * sizeof(float);
+    cluster_lookup_kernel<false><<<grid, PR_THREADS, smem, stream>>>(p);
+    STEGO_CHECK_LAUNCH("cluster_lookup_kernel<fwd>");
+  }
   sum_partials_kernel<<<1, 256, 0, stream>>>(scratch, grid, (float)(-1.0 / (double)total), loss_out);
   STEGO_CHECK_LAUNCH("sum_partials_kernel");
   return STEGO_OK;
@@ -413,10 +552,18 @@ extern "C" int stego_cluster_lookup_bwd(const float* x, long long stride_b, long
   p.grad_scale = (float)(-1.0 / (double)total);
   p.grad_loss = grad_loss_dev;
   p.dnc = dnc_scratch;
-  const int grid = cluster_grid(total);
-  const size_t smem = (size_t)(2 * n_classes * C + 8) * sizeof(float);
-  cluster_lookup_kernel<true><<<grid, PR_THREADS, smem, stream>>>(p);
-  STEGO_CHECK_LAUNCH("cluster_lookup_kernel<bwd>");
+  if (stride_c == 1 && n_classes <= 32 && !use_alpha) {
+    long long g = (total + 7) / 8;
+    const long long cap = 4ll * num_sms();
+    const int grid = (int)(g < cap ? g : cap);
+    cluster_lookup_cl_kernel<true><<<grid, 256, (size_t)(C * 32 + n_classes * C) * sizeof(float), stream>>>(p);
+    STEGO_CHECK_LAUNCH("cluster_lookup_cl_kernel<bwd>");
+  } else {
+    const int grid = cluster_grid(total);
+    const size_t smem = (size_t)(2 * n_classes * C + 8) * sizeof(float);
+    cluster_lookup_kernel<true><<<grid, PR_THREADS, smem, stream>>>(p);
+    STEGO_CHECK_LAUNCH("cluster_lookup_kernel<bwd>");
+  }
   cluster_norm_bwd_kernel<<<n_classes, 32, 0, stream>>>(clusters, dnc_scratch, dclusters, n_classes, C);
   STEGO_CHECK_LAUNCH("cluster_norm_bwd_kernel");
   return STEGO_OK;
@@ -438,8 +585,12 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
                   "stego_linear_probe_ce: C=%d n=%d unsupported", C, n_classes);
   STEGO_CHECK_ARG(!dlogits_scratch || (dW && db), "stego_linear_probe_ce: backward needs dW and db");
   const long long rows = 1ll * B * h * w;
-  linear_logits_kernel<<<(unsigned)((rows + 127) / 128), 128, (size_t)(n_classes * C + n_classes) * sizeof(float), stream>>>(
-      code, ld_code, C, W, bias, n_classes, logits_scratch, rows);
+  {
+    long long g = (rows + 7) / 8;
+    const long long capg = 16ll * num_sms();
+    linear_logits_kernel<<<(unsigned)(g < capg ? g : capg), 256, (size_t)C * 32 * sizeof(float), stream>>>(
+        code, ld_code, C, W, bias, n_classes, logits_scratch, rows);
+  }
   STEGO_CHECK_LAUNCH("linear_logits_kernel");
   LinearCEParams p;
   p.logits = logits_scratch; p.label = label; p.B = B; p.h = h; p.w = w; p.H = H; p.W = Wimg; p.n = n_classes;
@@ -472,10 +623,16 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   linear_ce_finish_kernel<<<1, 1, 0, stream>>>(p.acc, loss_out);
   STEGO_CHECK_LAUNCH("linear_ce_finish_kernel");
   if (dlogits_scratch) {
-    const int rpb = 256;
-    dim3 wg(n_classes, (unsigned)((rows + rpb - 1) / rpb));
-    linear_wgrad_kernel<<<wg, 128, 0, stream>>>(dlogits_scratch, code, ld_code, C, n_classes, rows, rpb, loss_out,
-                                                grad_loss, dW, db);
+    const unsigned blocks = (unsigned)((rows + LW_ROWS - 1) / LW_ROWS);
+    const size_t wsmem = (size_t)(LW_ROWS * 32 + LW_ROWS * C) * sizeof(float);
+    static size_t wconf = 0;
+    if (wsmem > 48 * 1024 && wsmem > wconf) {
+      cudaError_t e = cudaFuncSetAttribute(linear_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_wgrad)");
+      wconf = wsmem;
+    }
+    linear_wgrad_kernel<<<blocks, 256, wsmem, stream>>>(dlogits_scratch, code, ld_code, C, n_classes, rows, loss_out,
+                                                        grad_loss, dW, db);
     STEGO_CHECK_LAUNCH("linear_wgrad_kernel");
   }
   return STEGO_OK;
