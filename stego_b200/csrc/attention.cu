@@ -172,21 +172,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       mbar_wait(&s_full[wg], it & 1u);
       tc_fence_after();
       const uint32_t ts = TM_S + wg * ATT_BKV + lane_off;
-      // pass 1: row max
+      // the whole 64-key score row comes out of TMEM once and stays in registers for max, exp and packing
+      uint32_t v[2][32];
+      tmem_ld32(ts, v[0]);
+      tmem_ld32(ts + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[wg]);  // S buffer is free for the MMA warp as soon as it is in registers
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < ATT_BKV / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(ts + ch * 32, v);
-        tmem_ld_wait();
-        if (valid >= ch * 32 + 32) {
+      if (valid >= ATT_BKV) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
-        } else {
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[h][t]));
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int t = 0; t < 32; ++t)
-            if (ch * 32 + t < valid) mx = fmaxf(mx, __uint_as_float(v[t]));
-        }
+            if (h * 32 + t < valid) mx = fmaxf(mx, __uint_as_float(v[h][t]));
       }
       // lazy reference-max update: move it only on the first tile or when it is off by more than 2^8
       const bool first = (it == 0);
@@ -202,55 +207,45 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         mbar_wait(&o_full[wg], (it - 1u) & 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, move)) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld32(to + h * 32, v);
+#pragma unroll 1
+          for (int h = 0; h < ATT_D / 8; ++h) {  // rare path: 8 columns at a time keeps the register budget
+            uint32_t o[8];
+            tmem_ld8(to + h * 8, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
-            tmem_st32(to + h * 32, v);
+            for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+            tmem_st8(to + h * 8, o);
           }
           tmem_st_wait();
         }
       }
       const float mc = m_run * c;
-      // pass 2: p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem
+      // p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem (8 keys = one 16-byte chunk at a time)
       float rs = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < ATT_BKV / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(ts + ch * 32, v);
-        tmem_ld_wait();
-        float e[32];
-        if (valid >= ch * 32 + 32) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = ex2_approx(fmaf(__uint_as_float(v[t]), c, -mc));
-        } else {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = (ch * 32 + t < valid) ? ex2_approx(fmaf(__uint_as_float(v[t]), c, -mc)) : 0.f;
-        }
-        uint8_t* blk = sp;
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16x2(e[8 * g + 0], e[8 * g + 1]);
-          w.y = pack_bf16x2(e[8 * g + 2], e[8 * g + 3]);
-          w.z = pack_bf16x2(e[8 * g + 4], e[8 * g + 5]);
-          w.w = pack_bf16x2(e[8 * g + 6], e[8 * g + 7]);
-          *reinterpret_cast<uint4*>(blk + sw128_offset(r, ch * 4 + g)) = w;
+          float e[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) rs += e[8 * g + t];
+          for (int t = 0; t < 8; ++t) {
+            const float x = ex2_approx(fmaf(__uint_as_float(v[h][8 * g + t]), c, -mc));
+            e[t] = (valid >= ATT_BKV || h * 32 + 8 * g + t < valid) ? x : 0.f;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(e[0], e[1]);
+          w.y = pack_bf16x2(e[2], e[3]);
+          w.z = pack_bf16x2(e[4], e[5]);
+          w.w = pack_bf16x2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(sp + sw128_offset(r, h * 4 + g)) = w;
+          rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
         }
       }
       l_run += rs;
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[wg]);
-        mbar_arrive(&p_full[wg]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[wg]);
     }
     // ---- combine the two warpgroups (split-KV merge) and write the output ----
     // Both O accumulators live in the SAME TMEM lanes (rows), 64 columns apart, so warpgroup 0 reads both
