@@ -135,25 +135,51 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         umma_commit(&o_full[b]);
         umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
       };
-      uint32_t stage = 0, phase = 0;
-      for (int j = 0; j < nkv; ++j) {
-        const int b = j & 1;
-        const uint32_t it = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&kv_full[stage], phase);
-        mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
+      // Issue whatever is ready: S_js needs its K tile and a free S buffer (released as soon as the softmax warps
+      // hold the previous scores in registers); P V_jp needs P_jp.  Polling both keeps S two tiles ahead of the
+      // softmax instead of serialising "S_{j+1} after P_{j-1}" behind one blocking wait.
+      int js = 0, jp = 0;
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+      while (jp < nkv) {
+        bool progressed = false;
+        if (js < nkv) {
+          const int b = js & 1;
+          const uint32_t it = static_cast<uint32_t>(js >> 1);
+          const uint32_t stage = static_cast<uint32_t>(js % ATT_STAGES);
+          const uint32_t phase = static_cast<uint32_t>((js / ATT_STAGES) & 1);
+          if (mbar_try_wait(&kv_full[stage], phase) && mbar_try_wait(&s_empty[b], (it & 1u) ^ 1u)) {
+            tc_fence_after();
+            const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
-          umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
+            for (int k = 0; k < ATT_D / 16; ++k) {
+              const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
+              umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[b]);
+            ++js;
+            progressed = true;
+          }
         }
-        umma_commit(&s_full[b]);
-        if (j > 0) issue_pv(j - 1);
-        if (++stage == ATT_STAGES) { stage = 0; phase ^= 1u; }
+        if (jp < js) {
+          const uint32_t itp = static_cast<uint32_t>(jp >> 1);
+          if (mbar_try_wait(&p_full[jp & 1], itp & 1u)) {
+            issue_pv(jp);
+            ++jp;
+            progressed = true;
+          }
+        }
+        if (!progressed && ((++spins & 0xFFFFu) == 0)) {  // watchdog, as in mbar_wait
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > STEGO_MBAR_TIMEOUT_NS) {
+            printf("stego_b200: attention MMA issue loop timed out (block %d,%d,%d js %d jp %d)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, js, jp);
+            __trap();
+          }
+        }
       }
-      issue_pv(nkv - 1);
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -182,10 +208,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       if (lane == 0) mbar_arrive(&s_empty[wg]);  // S buffer is free for the MMA warp as soon as it is in registers
       float mx = -INFINITY;
       if (valid >= ATT_BKV) {
+        float m8[8];  // eight independent chains instead of one 64-long dependent chain
+#pragma unroll
+        for (int t = 0; t < 8; ++t) m8[t] = __uint_as_float(v[0][t]);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[h][t]));
+          for (int t = (h == 0 ? 8 : 0); t < 32; ++t) m8[t & 7] = fmaxf(m8[t & 7], __uint_as_float(v[h][t]));
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)

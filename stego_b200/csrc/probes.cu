@@ -320,19 +320,23 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   l1 = s - i0;
 }
 
-constexpr int LCE_TILE = 32;  // hi-res pixels per tile side
+constexpr int LCE_TILE = 16;  // hi-res pixels per tile side (256 threads = one per pixel)
 
-// One CTA per 32x32 tile of output pixels.  The low-res logits the tile can touch (its "box") are staged in
-// shared memory, the upsample + softmax + CE runs per pixel in registers, and the gradient wrt the low-res
-// logits is accumulated in a shared-memory box: lanes of a warp are 32 x-adjacent pixels, runs of lanes that
-// share the same taps are combined with a segmented shuffle reduction so that only run leaders touch the
-// (shared-memory) atomics; the box is flushed to global with one atomic per touched element.
+// One CTA per 16x16 tile of output pixels, three phases, no per-pixel atomics:
+//   1. thread = pixel: the low-res logits the tile can touch (its "box") are staged in shared memory; bilinear
+//      upsample + softmax + CE in registers; the per-pixel logit gradient g[pixel][k] goes to shared memory.
+//   2. the bilinear transpose is separable: T[Y][cx][k] = sum_X wx[X][cx] g[Y][X][k], then
+//      G[cy][cx][k] = sum_Y wy[Y][cy] T[Y][cx][k], each a conflict-free shared-memory reduction.
+//   3. one global atomic per (box cell, class) of the tile.
 __global__ void __launch_bounds__(256)
 linear_ce_kernel(LinearCEParams p) {
   extern __shared__ float sm[];
-  const int box_cap = p.box_h * p.box_w;
-  float* slog = sm;
-  float* sgrad = sm + box_cap * LP_LD;
+  const int bhm = p.box_h, bwm = p.box_w, n = p.n;
+  float* slog = sm;                                   // [box_h*box_w][LP_LD]
+  float* sg = slog + bhm * bwm * LP_LD;               // [256][n]   (odd stride n=27: conflict-free)
+  float* sT = sg + 256 * n;                           // [16][box_w][n]
+  float* swx = sT + LCE_TILE * bwm * n;               // [16][box_w]
+  float* swy = swx + LCE_TILE * bwm;                  // [16][box_h]
   __shared__ float sred[2][8];
   const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x;
@@ -349,95 +353,100 @@ linear_ce_kernel(LinearCEParams p) {
   src_index(Xl, sx, p.w, tmp, bx1, ftmp);
   const int bh = by1 - by0 + 1, bw = bx1 - bx0 + 1;  // <= box_h, box_w by construction on the host
   const long long base = 1ll * b * p.h * p.w;
-  for (int idx = threadIdx.x; idx < bh * bw * LP_LD; idx += blockDim.x) {
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < bh * bw * LP_LD; idx += 256) {
     const int k = idx % LP_LD, cell = idx / LP_LD;
     const int r = cell / bw, c = cell % bw;
-    slog[idx] = (k < p.n) ? p.logits[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k] : 0.f;
-    sgrad[idx] = 0.f;
+    slog[idx] = (k < n) ? p.logits[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k] : 0.f;
   }
+  for (int idx = tid; idx < LCE_TILE * bwm; idx += 256) swx[idx] = 0.f;
+  for (int idx = tid; idx < LCE_TILE * bhm; idx += 256) swy[idx] = 0.f;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // lanes = classes: lane k owns logit k of the pixel the warp is working on; the warp walks its rows pixel by
-  // pixel, softmax statistics are two warp reductions, and the gradient of the 4 low-res taps is kept in four
-  // per-lane registers that are flushed to the shared box only when the tap set changes (every H/h pixels).
-  const bool kact = lane < p.n;
-  float lsum = 0.f, cnt = 0.f;
-  for (int row = warp; row < LCE_TILE; row += 8) {
-    const int Y = Y0 + row;
-    if (Y >= p.H) break;
-    int y0, y1;
-    float ly;
+  // interpolation weights of the tile's rows / columns towards the box cells
+  if (tid < LCE_TILE) {
+    const int X = min(X0 + tid, p.W - 1);
+    int x0, x1; float lx;
+    src_index(X, sx, p.w, x0, x1, lx);
+    swx[tid * bwm + (x0 - bx0)] += 1.f - lx;
+    swx[tid * bwm + (x1 - bx0)] += lx;
+  } else if (tid < 2 * LCE_TILE) {
+    const int t = tid - LCE_TILE;
+    const int Y = min(Y0 + t, p.H - 1);
+    int y0, y1; float ly;
     src_index(Y, sy, p.h, y0, y1, ly);
-    const int r0 = (y0 - by0) * bw, r1 = (y1 - by0) * bw;
-    int cur00 = -1, cur11 = -1, cur01 = 0, cur10 = 0;
-    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-    const long long* lrow = p.label + (1ll * b * p.H + Y) * p.W;
-    for (int px = 0; px < LCE_TILE; ++px) {
-      const int X = X0 + px;
-      if (X >= p.W) break;
-      const long long lab = lrow[X];  // same address in every lane: one broadcast transaction
-      const bool valid = lab >= 0 && lab < p.n;
-      int x0, x1;
-      float lx;
-      src_index(X, sx, p.w, x0, x1, lx);
-      const int c00 = (r0 + x0 - bx0) * LP_LD, c01 = (r0 + x1 - bx0) * LP_LD;
-      const int c10 = (r1 + x0 - bx0) * LP_LD, c11 = (r1 + x1 - bx0) * LP_LD;
-      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-      if (p.dlogits && (c00 != cur00 || c11 != cur11)) {
-        if (cur00 >= 0 && kact) {
-          atomicAdd(&sgrad[cur00 + lane], a00);
-          atomicAdd(&sgrad[cur01 + lane], a01);
-          atomicAdd(&sgrad[cur10 + lane], a10);
-          atomicAdd(&sgrad[cur11 + lane], a11);
-        }
-        cur00 = c00; cur01 = c01; cur10 = c10; cur11 = c11;
-        a00 = a01 = a10 = a11 = 0.f;
-      }
-      if (!valid) continue;  // warp-uniform
-      const float z = kact ? (w00 * slog[c00 + lane] + w01 * slog[c01 + lane] + w10 * slog[c10 + lane] +
-                              w11 * slog[c11 + lane])
-                           : -INFINITY;
-      const float mx = warp_max(z);
-      const float e = kact ? expf(z - mx) : 0.f;
-      const float se = warp_sum(e);
-      const float zl = __shfl_sync(0xffffffffu, z, static_cast<int>(lab));
-      lsum += (mx + logf(se)) - zl;  // identical in every lane; lane 0's copy is used
-      cnt += 1.f;
-      if (p.dlogits) {
-        const float g = e / se - ((lane == lab) ? 1.f : 0.f);
-        a00 = fmaf(g, w00, a00);
-        a01 = fmaf(g, w01, a01);
-        a10 = fmaf(g, w10, a10);
-        a11 = fmaf(g, w11, a11);
+    swy[t * bhm + (y0 - by0)] += 1.f - ly;
+    swy[t * bhm + (y1 - by0)] += ly;
+  }
+  // ---- phase 1: thread = pixel
+  const int py = tid / LCE_TILE, px = tid % LCE_TILE;
+  const int Y = Y0 + py, X = X0 + px;
+  const bool inb = (Y < p.H) && (X < p.W);
+  long long lab = -1;
+  if (inb) lab = p.label[(1ll * b * p.H + Y) * p.W + X];
+  const bool valid = inb && lab >= 0 && lab < n;
+  float lsum = 0.f, cnt = 0.f;
+  {
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(min(Y, p.H - 1), sy, p.h, y0, y1, ly);
+    src_index(min(X, p.W - 1), sx, p.w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const int c00 = ((y0 - by0) * bw + (x0 - bx0)) * LP_LD, c01 = ((y0 - by0) * bw + (x1 - bx0)) * LP_LD;
+    const int c10 = ((y1 - by0) * bw + (x0 - bx0)) * LP_LD, c11 = ((y1 - by0) * bw + (x1 - bx0)) * LP_LD;
+    float z[LP_LD];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < LP_LD; ++k) {
+      if (k < n) {
+        z[k] = w00 * slog[c00 + k] + w01 * slog[c01 + k] + w10 * slog[c10 + k] + w11 * slog[c11 + k];
+        mx = fmaxf(mx, z[k]);
       }
     }
-    if (p.dlogits && cur00 >= 0 && kact) {
-      atomicAdd(&sgrad[cur00 + lane], a00);
-      atomicAdd(&sgrad[cur01 + lane], a01);
-      atomicAdd(&sgrad[cur10 + lane], a10);
-      atomicAdd(&sgrad[cur11 + lane], a11);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < LP_LD; ++k)
+      if (k < n) { z[k] = expf(z[k] - mx); se += z[k]; }   // z now holds exp(z - max)
+    const float inv = 1.0f / se;
+    if (valid) {
+      float el = 1.f;
+#pragma unroll
+      for (int k = 0; k < LP_LD; ++k)
+        if (k == lab) el = z[k];
+      lsum = -logf(el * inv);  // lse - z_lab
+      cnt = 1.f;
+    }
+    if (p.dlogits) {
+#pragma unroll
+      for (int k = 0; k < LP_LD; ++k)
+        if (k < n) sg[tid * n + k] = valid ? (z[k] * inv - ((k == lab) ? 1.f : 0.f)) : 0.f;
     }
   }
-  // every lane carries the same lsum / cnt: keep lane 0's
-  if (lane != 0) { lsum = 0.f; cnt = 0.f; }
   lsum = warp_sum(lsum);
   cnt = warp_sum(cnt);
-  if (lane == 0) { sred[0][warp] = lsum; sred[1][warp] = cnt; }
+  if ((tid & 31) == 0) { sred[0][tid >> 5] = lsum; sred[1][tid >> 5] = cnt; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     double a = 0, c = 0;
     for (int w = 0; w < 8; ++w) { a += sred[0][w]; c += sred[1][w]; }
     if (c > 0) { atomicAdd(p.acc, a); atomicAdd(p.acc + 1, c); }
   }
-  if (p.dlogits) {
-    for (int idx = threadIdx.x; idx < bh * bw * LP_LD; idx += blockDim.x) {
-      const float v = sgrad[idx];
-      if (v != 0.f) {
-        const int k = idx % LP_LD, cell = idx / LP_LD;
-        const int r = cell / bw, c = cell % bw;
-        atomicAdd(p.dlogits + (base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k, v);
-      }
-    }
+  if (!p.dlogits) return;
+  // ---- phase 2a: reduce over the tile's columns
+  for (int o = tid; o < LCE_TILE * bw * n; o += 256) {
+    const int k = o % n, cx = (o / n) % bw, yy = o / (n * bw);
+    float acc = 0.f;
+#pragma unroll
+    for (int xx = 0; xx < LCE_TILE; ++xx) acc = fmaf(swx[xx * bwm + cx], sg[(yy * LCE_TILE + xx) * n + k], acc);
+    sT[(yy * bwm + cx) * n + k] = acc;
+  }
+  __syncthreads();
+  // ---- phase 2b + 3: reduce over the rows, one atomic per (cell, class)
+  for (int o = tid; o < bh * bw * n; o += 256) {
+    const int k = o % n, cx = (o / n) % bw, cy = o / (n * bw);
+    float acc = 0.f;
+#pragma unroll
+    for (int yy = 0; yy < LCE_TILE; ++yy) acc = fmaf(swy[yy * bhm + cy], sT[(yy * bwm + cx) * n + k], acc);
+    if (acc != 0.f) atomicAdd(p.dlogits + (base + 1ll * (by0 + cy) * p.w + bx0 + cx) * LP_LD + k, acc);
   }
 }
 
@@ -603,7 +612,8 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   p.box_w = (int)((double)LCE_TILE * w / Wimg) + 3;
   if (p.box_h > h) p.box_h = h;
   if (p.box_w > w) p.box_w = w;
-  const size_t ce_smem = (size_t)2 * p.box_h * p.box_w * LP_LD * sizeof(float);
+  const size_t ce_smem = ((size_t)p.box_h * p.box_w * LP_LD + 256 * (size_t)n_classes + (size_t)LCE_TILE * p.box_w * n_classes +
+                          (size_t)LCE_TILE * (p.box_w + p.box_h)) * sizeof(float);
   STEGO_CHECK_ARG(ce_smem <= 200 * 1024, "stego_linear_probe_ce: upsample ratio %dx%d -> %dx%d needs %zu B of smem", h, w, H, Wimg, ce_smem);
   {
     static size_t configured = 0;

@@ -172,15 +172,17 @@ class _HeadFn(torch.autograd.Function):
         dyb = torch.empty(M, 128, dtype=torch.bfloat16, device=dev)
         _lib.check(lib.stego_cast_pad_bf16(_lib.ptr(dcode), dcode.stride(0), D, _lib.ptr(dyb), 128, M, _lib.stream()),
                    "stego_cast_pad_bf16")
-        splits = max(1, min(64, M // 512))
+        def splits_for(out_rows, out_cols):
+            tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
+            return max(1, min(64, M // 512, -(-296 // tiles)))  # ~2 CTAs per SM, bounded atomic fan-in
         db = torch.zeros(D, dtype=torch.float32, device=dev)
         _lib.check(lib.stego_colsum(_lib.ptr(dcode), 0, dcode.stride(0), D, M, _lib.ptr(db), _lib.stream()), "stego_colsum")
         dw1 = torch.zeros(D, E, dtype=torch.float32, device=dev)
-        ops.gemm(dyb, x1, dw1, M=D, N=E, K=M, a_mn=True, b_mn=True, splits=splits, atomic=True)
+        ops.gemm(dyb, x1, dw1, M=D, N=E, K=M, a_mn=True, b_mn=True, splits=splits_for(D, E), atomic=True)
         dwa = dba = dwb = dbb = None
         if nonlinear:
             dwb = torch.zeros(D, E, dtype=torch.float32, device=dev)
-            ops.gemm(dyb, hid, dwb, M=D, N=E, K=M, a_mn=True, b_mn=True, splits=splits, atomic=True)
+            ops.gemm(dyb, hid, dwb, M=D, N=E, K=M, a_mn=True, b_mn=True, splits=splits_for(D, E), atomic=True)
             dbb = db.clone()
             # dH = dY . Wb  (B operand [K=c][N=E] is MN-major), then ReLU backward -> bf16 operand
             dh = torch.empty(M, E, dtype=torch.float32, device=dev)
@@ -191,7 +193,7 @@ class _HeadFn(torch.autograd.Function):
             dba = torch.zeros(E, dtype=torch.float32, device=dev)
             _lib.check(lib.stego_colsum(_lib.ptr(dhb), 1, E, E, M, _lib.ptr(dba), _lib.stream()), "stego_colsum")
             dwa = torch.zeros(E, E, dtype=torch.float32, device=dev)
-            ops.gemm(dhb, x2, dwa, M=E, N=E, K=M, a_mn=True, b_mn=True, splits=splits, atomic=True)
+            ops.gemm(dhb, x2, dwa, M=E, N=E, K=M, a_mn=True, b_mn=True, splits=splits_for(E, E), atomic=True)
         s1, sa, sb_ = ctx.shapes
         return (None, None, None, None, None, dw1.reshape(s1), db,
                 dwa.reshape(sa) if nonlinear else None, dba, dwb.reshape(sb_) if nonlinear else None, dbb)
