@@ -148,7 +148,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
           const uint32_t it = static_cast<uint32_t>(js >> 1);
           const uint32_t stage = static_cast<uint32_t>(js % ATT_STAGES);
           const uint32_t phase = static_cast<uint32_t>((js / ATT_STAGES) & 1);
-          if (mbar_try_wait(&kv_full[stage], phase) && mbar_try_wait(&s_empty[b], (it & 1u) ^ 1u)) {
+          if (mbar_test_wait(&kv_full[stage], phase) && mbar_test_wait(&s_empty[b], (it & 1u) ^ 1u)) {
             tc_fence_after();
             const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
 #pragma unroll
@@ -164,7 +164,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         }
         if (jp < js) {
           const uint32_t itp = static_cast<uint32_t>(jp >> 1);
-          if (mbar_try_wait(&p_full[jp & 1], itp & 1u)) {
+          if (mbar_test_wait(&p_full[jp & 1], itp & 1u)) {
             issue_pv(jp);
             ++jp;
             progressed = true;

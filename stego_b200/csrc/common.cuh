@@ -75,6 +75,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking probe (try_wait may suspend the thread for a hardware time slice; test_wait never does) — for loops
+// that poll several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 #ifndef STEGO_MBAR_TIMEOUT_NS
 #define STEGO_MBAR_TIMEOUT_NS 4000000000ull  // 4 s: a deadlock becomes a trap, never a hung GPU
 #endif
