@@ -135,50 +135,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         umma_commit(&o_full[b]);
         umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
       };
-      // Issue whatever is ready: S_js needs its K tile and a free S buffer (released as soon as the softmax warps
-      // hold the previous scores in registers); P V_jp needs P_jp.  Polling both keeps S two tiles ahead of the
-      // softmax instead of serialising "S_{j+1} after P_{j-1}" behind one blocking wait.
-      int js = 0, jp = 0;
-      uint64_t t0 = 0;
-      uint32_t spins = 0;
-      while (jp < nkv) {
-        bool progressed = false;
-        if (js < nkv) {
-          const int b = js & 1;
-          const uint32_t it = static_cast<uint32_t>(js >> 1);
-          const uint32_t stage = static_cast<uint32_t>(js % ATT_STAGES);
-          const uint32_t phase = static_cast<uint32_t>((js / ATT_STAGES) & 1);
-          if (mbar_test_wait(&kv_full[stage], phase) && mbar_test_wait(&s_empty[b], (it & 1u) ^ 1u)) {
-            tc_fence_after();
-            const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
+      // S runs two tiles ahead of P V: the S buffer of tile j+2 is free as soon as the softmax warpgroup holds the
+      // scores of tile j in registers (early s_empty), so S_{j+2} is issued BEFORE the blocking wait for P_j and is
+      // ready when that warpgroup comes back.  (Blocking try_wait on purpose: a polling loop on this lane steals
+      // issue slots from the softmax warps of its SM sub-partition.)
+      auto issue_s = [&](int j) {
+        const int b = j & 1;
+        const uint32_t it = static_cast<uint32_t>(j >> 1);
+        const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
+        const uint32_t phase = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+        mbar_wait(&kv_full[stage], phase);
+        mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
 #pragma unroll
-            for (int k = 0; k < ATT_D / 16; ++k) {
-              const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
-              umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
-            }
-            umma_commit(&s_full[b]);
-            ++js;
-            progressed = true;
-          }
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
+          umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
         }
-        if (jp < js) {
-          const uint32_t itp = static_cast<uint32_t>(jp >> 1);
-          if (mbar_test_wait(&p_full[jp & 1], itp & 1u)) {
-            issue_pv(jp);
-            ++jp;
-            progressed = true;
-          }
-        }
-        if (!progressed && ((++spins & 0xFFFFu) == 0)) {  // watchdog, as in mbar_wait
-          const uint64_t now = globaltimer_ns();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > STEGO_MBAR_TIMEOUT_NS) {
-            printf("stego_b200: attention MMA issue loop timed out (block %d,%d,%d js %d jp %d)\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, js, jp);
-            __trap();
-          }
-        }
+        umma_commit(&s_full[b]);
+      };
+      issue_s(0);
+      if (nkv > 1) issue_s(1);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 2 < nkv) issue_s(j + 2);
+        issue_pv(j);
       }
     }
   } else {
