@@ -20,6 +20,8 @@
 // Input is the packed qkv GEMM output [B, N, 3E] bf16 (q | k | v, head-major inside each), read through
 // ONE 3-D tensor map; rows past N (ragged last tile: N = hw + 1 is never a multiple of 128) are
 // zero-filled by TMA and masked to -inf in the softmax.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -28,7 +30,7 @@ namespace stego {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;   // 64-key tiles: 6 % padding waste at N = 785 (128-key tiles waste 14 %), half the smem
 constexpr int ATT_D = 64;
-constexpr int ATT_STAGES = 3;
+constexpr int ATT_STAGES = 4;
 constexpr int ATT_THREADS = 320;
 constexpr uint32_t ATT_TMEM_COLS = 256;  // S: 2 x 64, O: 2 x 64 -> two CTAs fit the 512 columns of an SM
 
@@ -38,21 +40,24 @@ constexpr uint32_t ATT_P_BYTES = 128 * 64 * 2;   // 16 KB [128 q][64 kv]
 constexpr uint32_t ATT_SMEM_Q = 0;
 constexpr uint32_t ATT_SMEM_KV = ATT_Q_BYTES;                                   // stages x (K,V)
 constexpr uint32_t ATT_SMEM_P = ATT_SMEM_KV + ATT_STAGES * 2 * ATT_KV_BYTES;    // one P tile per warpgroup
-constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_P + 2 * ATT_P_BYTES;                  // m,l of WG1: 2 x 128 floats
-constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_ML + 1024;
-constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256 + 1024;  // ~98 KB incl. alignment slack: 2 CTAs per SM
+constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_Q;  // m,l of WG1 (2 x 128 floats) reuse the Q tile once every S has been issued
+constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_P + 2 * ATT_P_BYTES;
+constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256;  // 112.25 KB: two CTAs per SM (<= 113 KB each)
 
 struct AttnParams {
   bf16* out;   // [B*N][E] bf16 (heads concatenated, like .transpose(1,2).reshape(B,N,C))
   int N;       // tokens per image
   int E;       // embed dim = heads * 64
   float scale_log2e;  // head_dim^-0.5 * log2(e)
+  int s_ahead;        // how many KV tiles S = QK^T is issued ahead of P V (1 or 2)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic window starts at offset 0 of the CTA's allocation and the
+  // __align__(1024) below is honoured (128B-swizzled tiles need 1024-byte alignment); checked at run time.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
   uint64_t* q_full = bars;                        // [1]
   uint64_t* kv_full = bars + 1;                   // [STAGES]
@@ -156,10 +161,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         }
         umma_commit(&s_full[b]);
       };
-      issue_s(0);
-      if (nkv > 1) issue_s(1);
+      const int ahead = p.s_ahead;
+      for (int j = 0; j < ahead && j < nkv; ++j) issue_s(j);
       for (int j = 0; j < nkv; ++j) {
-        if (j + 2 < nkv) issue_s(j + 2);
+        if (j + ahead < nkv) issue_s(j + ahead);
         issue_pv(j);
       }
     }
@@ -264,6 +269,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     // straight out of TMEM; only m and l of warpgroup 1 travel through shared memory.
     float* ml = reinterpret_cast<float*>(smem + ATT_SMEM_ML);  // [2][128]
     if (wg == 1) {
+      // ml aliases the Q tile: every S = Q K^T must have retired first.  tcgen05.commit covers all earlier MMAs of
+      // the issuing thread, and every S is issued before this warpgroup's last P V, so its o_full is sufficient
+      // (with no tile of its own — a single KV tile — wait for S_0 instead).
+      if (it > 0) mbar_wait(&o_full[1], (it - 1u) & 1u);
+      else mbar_wait(&s_full[0], 0);
       ml[r] = m_run;
       ml[128 + r] = l_run;
     }
@@ -345,6 +355,14 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
   p.N = N;
   p.E = E;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
+  {
+    static int ahead = 0;
+    if (ahead == 0) {
+      const char* e = getenv("STEGO_ATT_S_AHEAD");
+      ahead = (e && e[0] == '1') ? 1 : 2;
+    }
+    p.s_ahead = ahead;
+  }
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, p);
   STEGO_CHECK_LAUNCH("attention_fwd_kernel");

@@ -81,13 +81,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "BN must be 128 or 256");
-  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+  // BN = 128 / 256: two accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1).
+  // BN = 384 (a whole E = 384 row block per CTA: A is read ONCE instead of three times): one 384-column
+  // accumulator (TMEM has 512 columns), two MMAs per k-step (N = 256 + 128), single epilogue staging tile.
+  static_assert(BN == 128 || BN == 256 || BN == 384, "BN must be 128, 256 or 384");
+  constexpr uint32_t kAccBufs = (BN == 384) ? 1u : 2u;
+  constexpr uint32_t kEpiBufs = (BN == 384) ? 1u : 2u;
+  constexpr uint32_t TMEM_COLS = (BN == 128) ? 256u : 512u;
+  constexpr uint32_t N0 = (BN == 384) ? 256u : static_cast<uint32_t>(BN);  // first MMA of a k-step
+  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, N0, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+  constexpr uint32_t IDESC_TAIL = make_idesc_bf16(GEMM_BM, 128, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+  static_assert(BN != 384 || (!A_MN && !B_MN), "384-wide tiles are K-major only");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr uint32_t EPI_BYTES = 8 * 2 * 4096;  // two 32-row x 128-byte staging tiles per epilogue warp
+  constexpr uint32_t EPI_BYTES = 8 * kEpiBufs * 4096;  // 32-row x 128-byte staging tiles per epilogue warp
   uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
@@ -146,7 +154,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN);
+#pragma unroll
+            for (int blk = 0; blk < BN / 128; ++blk)  // tensor-map box = 128 rows
+              tma_load_2d(sb + blk * 16384, &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * 128);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / 64; ++blk)
@@ -167,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * (TMEM_COLS / kAccBufs);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -182,12 +192,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                      : make_smem_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BN == 384)  // columns 256..383 of the accumulator <- B rows 256..383
+              umma_bf16(tmem_d + 256, da, make_smem_desc_sw128(sb + 256 * 128 + k * 32, 16, 1024), IDESC_TAIL,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -219,12 +232,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         out_row = row + row / p.row_div + 1;
         res_row = row % p.row_div + 1;
       }
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * (TMEM_COLS / kAccBufs) + (static_cast<uint32_t>(quarter * 32) << 16);
       if (p.tma_epi) {
         // ---- TMA epilogue: TMEM -> regs (bias/act) -> swizzled smem staging tile -> ONE bulk tensor store (or fp32
         //      reduce-add for the in-place residual update x += ...) per 32 x 128-byte tile.  No global load/store
         //      instructions, edges clipped by the tensor map, staging double-buffered per warp.
-        uint8_t* buf0 = epi_smem + (warp - 2) * 8192;
+        uint8_t* buf0 = epi_smem + (warp - 2) * (kEpiBufs * 4096);
         const int row_base = tm * GEMM_BM + quarter * 32;
         if (p.out_bf16) {
 #pragma unroll 1
@@ -234,8 +247,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t v0[32], v1[32];
             tmem_ld32(taddr + c * 64, v0);
             tmem_ld32(taddr + c * 64 + 32, v1);
-            uint8_t* buf = buf0 + (epi_groups & 1u) * 4096;
-            if (lane == 0) tma_wait_group_read<1>();  // the store that last read this staging tile is done with it
+            uint8_t* buf = buf0 + (epi_groups & (kEpiBufs - 1u)) * 4096;
+            if (lane == 0) tma_wait_group_read<kEpiBufs - 1>();  // the store that last read this staging tile is done with it
             __syncwarp();
             tmem_ld_wait();
 #pragma unroll
@@ -284,8 +297,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (col0 >= p.N) break;
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
-            uint8_t* buf = buf0 + (epi_groups & 1u) * 4096;
-            if (lane == 0) tma_wait_group_read<1>();
+            uint8_t* buf = buf0 + (epi_groups & (kEpiBufs - 1u)) * 4096;
+            if (lane == 0) tma_wait_group_read<kEpiBufs - 1>();
             __syncwarp();
             tmem_ld_wait();
             float x[32];
@@ -322,7 +335,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
       if (p.fast_epi) {
@@ -446,7 +459,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
 #pragma unroll 1
@@ -523,7 +536,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -539,7 +552,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int kStages, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * 2 * 4096 + 1024 + 256;
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * (BN == 384 ? 1 : 2) * 4096 + 1024 + 256;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
@@ -613,7 +626,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   {
     uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, b_mn_major ? 64u : (wide ? 256u : 128u)};
+    uint32_t box[2] = {64, b_mn_major ? 64u : 128u};
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
   if (p.tma_epi) {
@@ -625,6 +638,9 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   } else {
     tmO = tmA;  // unused
   }
+  // N == 384 (ViT-S proj / fc2, in-place residual): one 128 x 384 tile per CTA reads each A row block once
+  if (p.tma_epi && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && splits == 1)
+    return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);
