@@ -195,14 +195,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       if (lane == 0) mbar_arrive(&s_empty[wg]);  // S buffer is free for the MMA warp as soon as it is in registers
       float mx = -INFINITY;
       if (valid >= ATT_BKV) {
-        float m8[8];  // eight independent chains instead of one 64-long dependent chain
-#pragma unroll
-        for (int t = 0; t < 8; ++t) m8[t] = __uint_as_float(v[0][t]);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int t = (h == 0 ? 8 : 0); t < 32; ++t) m8[t & 7] = fmaxf(m8[t & 7], __uint_as_float(v[h][t]));
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[h][t]));  // FMNMX3 chain (a hand-made tree was slower)
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)

@@ -639,7 +639,8 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     tmO = tmA;  // unused
   }
   // N == 384 (ViT-S proj / fc2, in-place residual): one 128 x 384 tile per CTA reads each A row block once
-  if (p.tma_epi && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && splits == 1)
+  // (only worth it when the mainloop dominates: the single accumulator cannot overlap epilogue and MMAs)
+  if (p.tma_epi && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1)
     return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
