@@ -82,12 +82,14 @@ STEGO_API int stego_attention_fwd(const void* qkv, void* out, int B, int N, int 
 /* sample (:287-288) + norm (:275-276): bilinear border/align_corners=True gather at the coords, optional
  * per-(image,channel) scale (the Dropout2d noise of modules.py:116), L2 normalise (eps 1e-10), write
  * the hi/lo split tiles.  src strides are in elements; coords are [B][fs][fs][2] fp32;
- * perms [nslots-2][B] int64 (already super_perm'ed, :291-295). */
+ * perms [nslots-2][B] int64: super_perm results (:291-295), or — perms_are_raw_randperm = 1 — the raw randperm
+ * draws, in which case the kernel applies super_perm's fix-up (p == b -> (p + 1) % B) itself. */
 STEGO_API int stego_sample_norm_fwd(const void* src, const void* src_pos, int src_is_bf16, long long stride_b,
                                     long long stride_c, long long stride_y, long long stride_x,
                                     const float* chan_scale, const float* chan_scale_pos, const float* coords1,
                                     const float* coords2, const long long* perms, void* tiles, int B, int C,
-                                    int Cpad, int H, int W, int feature_samples, int nslots, void* stream);
+                                    int Cpad, int H, int W, int feature_samples, int nslots, int perms_are_raw_randperm,
+                                    void* stream);
 /* helper (:325-347) for all calls at once: fd and cd einsums on tcgen05 (bf16 hi/lo split, fp32 accumulate),
  * pointwise centring, clamp, shift, product and reduction.  slot_of_call / shifts are HOST arrays.
  * partials: scratch [ncalls][B][8]; stats: out [ncalls][4] = {mean loss, mean cd, old_mean, mean of centred fd}.
@@ -110,7 +112,7 @@ STEGO_API int stego_sample_norm_bwd(const float* code, const float* code_pos, lo
                                     long long stride_y, long long stride_x, const float* coords1,
                                     const float* coords2, const long long* perms, const float* dtiles, float* dcode,
                                     float* dcode_pos, int B, int C, int H, int W, int feature_samples, int nslots,
-                                    void* stream);
+                                    int perms_are_raw_randperm, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Segmentation head glue (reference: src/modules.py:73-81, 108-118) and optimiser

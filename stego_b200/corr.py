@@ -61,7 +61,8 @@ class LossSpec:
 
 def build_tiles(src: torch.Tensor, src_pos: torch.Tensor, coords1: torch.Tensor, coords2: torch.Tensor,
                 perms: Optional[torch.Tensor], spec: LossSpec, c_pad: int,
-                chan_scale: Optional[torch.Tensor] = None, chan_scale_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+                chan_scale: Optional[torch.Tensor] = None, chan_scale_pos: Optional[torch.Tensor] = None,
+                raw_perms: bool = False) -> torch.Tensor:
     """sample + norm for every slot -> bf16 hi/lo tiles [2][nslots][B][128][c_pad]."""
     B, C, H, W = src.shape
     src_pos = _same_layout(src, src_pos)
@@ -70,7 +71,7 @@ def build_tiles(src: torch.Tensor, src_pos: torch.Tensor, coords1: torch.Tensor,
     rc = _lib.load().stego_sample_norm_fwd(
         _lib.ptr(src), _lib.ptr(src_pos), int(src.dtype == torch.bfloat16), sb, sc, sy, sx,
         _lib.ptr(chan_scale), _lib.ptr(chan_scale_pos), _lib.ptr(coords1), _lib.ptr(coords2), _lib.ptr(perms),
-        _lib.ptr(tiles), B, C, c_pad, H, W, spec.fs, spec.nslots, _lib.stream())
+        _lib.ptr(tiles), B, C, c_pad, H, W, spec.fs, spec.nslots, int(raw_perms), _lib.stream())
     _lib.check(rc, "stego_sample_norm_fwd")
     return tiles
 
@@ -103,7 +104,7 @@ class _CorrLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, code, code_pos, feats, feats_pos, coords1, coords2, perms, spec: LossSpec, want_elems: bool,
-                chan_scale, chan_scale_pos):
+                chan_scale, chan_scale_pos, raw_perms=False):
         B, E, D, H, W, coords1, coords2, perms_t = _prep_common(feats, feats_pos, code, code_pos, coords1, coords2,
                                                                  perms, spec)
         code_f = code.detach()
@@ -112,8 +113,9 @@ class _CorrLossFn(torch.autograd.Function):
         code_pos_f = _same_layout(code_f, code_pos.detach().to(torch.float32))
         dev = code.device
         ftiles = build_tiles(feats.detach(), feats_pos.detach(), coords1, coords2, perms_t, spec, E, chan_scale,
-                             chan_scale_pos)
-        ctiles = build_tiles(code_f, code_pos_f, coords1, coords2, perms_t, spec, CODE_PAD)
+                             chan_scale_pos, raw_perms)
+        ctiles = build_tiles(code_f, code_pos_f, coords1, coords2, perms_t, spec, CODE_PAD, raw_perms=raw_perms)
+        ctx.raw_perms = bool(raw_perms)
         S = spec.fs * spec.fs
         partials = torch.empty(spec.ncalls, B, 8, dtype=torch.float32, device=dev)
         stats = torch.empty(spec.ncalls, 4, dtype=torch.float32, device=dev)
@@ -163,15 +165,17 @@ class _CorrLossFn(torch.autograd.Function):
         rc = _lib.load().stego_sample_norm_bwd(
             _lib.ptr(code_f), _lib.ptr(code_pos_f), sb, sc, sy, sx, _lib.ptr(coords1), _lib.ptr(coords2),
             _lib.ptr(perms_arg), _lib.ptr(dtiles), _lib.ptr(dcode), _lib.ptr(dcode_pos), B, D, H, W, spec.fs,
-            spec.nslots, _lib.stream())
+            spec.nslots, int(ctx.raw_perms), _lib.stream())
         _lib.check(rc, "stego_sample_norm_bwd")
         d0, d1 = ctx.code_dtype
-        return (dcode.to(d0), dcode_pos.to(d1), None, None, None, None, None, None, None, None, None)
+        return (dcode.to(d0), dcode_pos.to(d1), None, None, None, None, None, None, None, None, None, None)
 
 
 def corr_loss(feats, feats_pos, code, code_pos, coords1, coords2, perms, spec: LossSpec, want_elems: bool = False,
-              chan_scale=None, chan_scale_pos=None):
-    """Returns (losses[ncalls], cd_means[ncalls], cd[ncalls,B,S,S]|None, loss_elems|None).
+              chan_scale=None, chan_scale_pos=None, raw_perms: bool = False):
+    """raw_perms=True: `perms` holds the raw torch.randperm draws and the sampling kernel applies super_perm's
+    fix-up itself (saves the eq/add/remainder launches of modules.super_perm).
+    Returns (losses[ncalls], cd_means[ncalls], cd[ncalls,B,S,S]|None, loss_elems|None).
     losses[k] is the mean of helper call k (0 intra, 1 inter, 2.. negatives); differentiable wrt code/code_pos."""
     return _CorrLossFn.apply(code, code_pos, feats, feats_pos, coords1, coords2, perms, spec, want_elems,
-                             chan_scale, chan_scale_pos)
+                             chan_scale, chan_scale_pos, raw_perms)

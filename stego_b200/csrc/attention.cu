@@ -175,6 +175,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const int r = quarter * 32 + lane;  // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* sp = smem + ATT_SMEM_P + wg * ATT_P_BYTES;
+    const bool warp_has_rows = (q0 + quarter * 32) < p.N;
     float m_run = -INFINITY, l_run = 0.f;  // m_run: reference max the exponentials are taken against
     const float c = p.scale_log2e;
     const uint32_t to = TM_O + wg * 64 + lane_off;
@@ -184,6 +185,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       const int valid = p.N - j * ATT_BKV;  // number of real keys in this tile (>= 1)
       mbar_wait(&s_full[wg], it & 1u);
       tc_fence_after();
+      if (!warp_has_rows) {
+        // ragged last query tile (N = hw + 1): this warp's 32 rows are all padding — keep the barrier protocol,
+        // skip the loads / exponentials / stores (their P rows and O rows are never read back)
+        if (lane == 0) mbar_arrive(&s_empty[wg]);
+        if (it > 0) mbar_wait(&o_full[wg], (it - 1u) & 1u);
+        if (lane == 0) mbar_arrive(&p_full[wg]);
+        continue;
+      }
       const uint32_t ts = TM_S + wg * ATT_BKV + lane_off;
       // the whole 64-key score row comes out of TMEM once and stays in registers for max, exp and packing
       uint32_t v[2][32];

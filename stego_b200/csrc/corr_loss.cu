@@ -45,6 +45,7 @@ struct SampleParams {
   const float* coords1;  // [B][fs][fs][2]
   const float* coords2;
   const long long* perms;  // [nslots-2][B]
+  int perms_raw;           // 1: perms are raw randperm draws; apply super_perm's fix-up (p == b -> (p+1) % B) here
   bf16* tiles;             // [2 planes][nslots][B][128][Cpad]
   int B, C, Cpad, H, W, fs, S, nslots;
   float eps;
@@ -86,7 +87,11 @@ __device__ __forceinline__ void slot_source(const SampleParams& p, int slot, int
                                             const float*& cscale, const float*& coords, int& img) {
   if (slot == 0) { src = p.src; cscale = p.chan_scale; coords = p.coords1; img = b; }
   else if (slot == 1) { src = p.src_pos; cscale = p.chan_scale_pos; coords = p.coords2; img = b; }
-  else { src = p.src; cscale = p.chan_scale; coords = p.coords2; img = static_cast<int>(p.perms[(slot - 2) * p.B + b]); }
+  else {
+    src = p.src; cscale = p.chan_scale; coords = p.coords2;
+    img = static_cast<int>(p.perms[(slot - 2) * p.B + b]);
+    if (p.perms_raw && img == b) img = (img + 1) % p.B;  // modules.py:291-295
+  }
 }
 
 // One warp per tile row. Generic strides / dtypes; each lane owns channels lane, lane+32, ...
@@ -686,7 +691,7 @@ static int fill_sample_params(SampleParams& sp, const void* src, const void* src
   sp.src = src; sp.src_pos = src_pos; sp.src_bf16 = src_bf16;
   sp.sb = sb; sp.sc = sc; sp.sy = sy; sp.sx = sx;
   sp.chan_scale = chan_scale; sp.chan_scale_pos = chan_scale_pos;
-  sp.coords1 = coords1; sp.coords2 = coords2; sp.perms = perms;
+  sp.coords1 = coords1; sp.coords2 = coords2; sp.perms = perms; sp.perms_raw = 0;
   sp.tiles = reinterpret_cast<bf16*>(tiles);
   sp.B = B; sp.C = C; sp.Cpad = Cpad; sp.H = H; sp.W = W; sp.fs = fs; sp.S = fs * fs; sp.nslots = nslots;
   sp.eps = 1e-10f;
@@ -701,12 +706,14 @@ extern "C" int stego_sample_norm_fwd(const void* src, const void* src_pos, int s
                                      long long stride_c, long long stride_y, long long stride_x,
                                      const float* chan_scale, const float* chan_scale_pos, const float* coords1,
                                      const float* coords2, const long long* perms, void* tiles, int B, int C,
-                                     int Cpad, int H, int W, int feature_samples, int nslots, void* stream_) {
+                                     int Cpad, int H, int W, int feature_samples, int nslots, int perms_are_raw_randperm,
+                                     void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SampleParams sp;
   int rc = fill_sample_params(sp, src, src_pos, src_is_bf16, stride_b, stride_c, stride_y, stride_x, chan_scale,
                               chan_scale_pos, coords1, coords2, perms, tiles, B, C, Cpad, H, W, feature_samples, nslots);
   if (rc != STEGO_OK) return rc;
+  sp.perms_raw = perms_are_raw_randperm;
   STEGO_CHECK_ARG(tiles, "stego_sample_norm_fwd: null tiles");
   const int warps = nslots * B * CL_ROWS;
   const int blocks = (warps + 7) / 8;
@@ -822,7 +829,7 @@ extern "C" int stego_sample_norm_bwd(const float* code, const float* code_pos, l
                                      long long stride_y, long long stride_x, const float* coords1,
                                      const float* coords2, const long long* perms, const float* dtiles, float* dcode,
                                      float* dcode_pos, int B, int C, int H, int W, int feature_samples, int nslots,
-                                     void* stream_) {
+                                     int perms_are_raw_randperm, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(dtiles && dcode && dcode_pos, "stego_sample_norm_bwd: null pointer");
   STEGO_CHECK_ARG(C <= 96, "stego_sample_norm_bwd: C=%d unsupported (<= 96)", C);
@@ -830,6 +837,7 @@ extern "C" int stego_sample_norm_bwd(const float* code, const float* code_pos, l
   int rc = fill_sample_params(q.f, code, code_pos, 0, stride_b, stride_c, stride_y, stride_x, nullptr, nullptr,
                               coords1, coords2, perms, nullptr, B, C, CL_CODE_PAD, H, W, feature_samples, nslots);
   if (rc != STEGO_OK) return rc;
+  q.f.perms_raw = perms_are_raw_randperm;
   q.dtiles = dtiles; q.dsrc = dcode; q.dsrc_pos = dcode_pos;
   const int warps = nslots * B * q.f.S;
   sample_norm_bwd_kernel<3><<<(warps + 7) / 8, 256, 0, stream>>>(q);

@@ -405,14 +405,14 @@ linear_ce_kernel(LinearCEParams p) {
     float se = 0.f;
 #pragma unroll
     for (int k = 0; k < LP_LD; ++k)
-      if (k < n) { z[k] = expf(z[k] - mx); se += z[k]; }   // z now holds exp(z - max)
+      if (k < n) { z[k] = __expf(z[k] - mx); se += z[k]; }   // z now holds exp(z - max)  (ex2.approx: 2 ulp)
     const float inv = 1.0f / se;
     if (valid) {
       float el = 1.f;
 #pragma unroll
       for (int k = 0; k < LP_LD; ++k)
         if (k == lab) el = z[k];
-      lsum = -logf(el * inv);  // lse - z_lab
+      lsum = -__logf(el * inv);  // lse - z_lab
       cnt = 1.f;
     }
     if (p.dlogits) {

@@ -269,12 +269,14 @@ class LitUnsupervisedSegmenter(nn.Module):
             salience_pos = batch["mask_pos"].to(torch.float32).squeeze(1) if cfg.use_salience else None
             lossfn = self.contrastive_corr_loss_fn
             coords1, coords2 = lossfn.draw_coords(feats, salience, salience_pos)
-            from .modules import super_perm
-            perms = [super_perm(B, img.device) for _ in range(cfg.neg_samples)]
+            # same RNG calls as modules.super_perm (randperm per negative); its fix-up runs inside the sampling kernel
+            perms = torch.empty(cfg.neg_samples, B, dtype=torch.long, device=img.device)
+            for i in range(cfg.neg_samples):
+                torch.randperm(B, device=img.device, dtype=torch.long, out=perms[i])
             # the returned-feature dropout (modules.py:116) is folded into the sampling kernel (chan_scale)
             losses, cd_means, _, _ = corr.corr_loss(feats, feats_pos, code, code_pos, coords1, coords2, perms, self._spec,
                                                     want_elems=False, chan_scale=m3 if cfg.dropout else None,
-                                                    chan_scale_pos=p3 if cfg.dropout else None)
+                                                    chan_scale_pos=p3 if cfg.dropout else None, raw_perms=True)
             pos_intra_loss, pos_inter_loss = losses[0], losses[1]
             neg_inter_loss = losses[2:].mean()
             self.log('loss/pos_intra', pos_intra_loss)
