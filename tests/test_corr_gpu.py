@@ -143,3 +143,57 @@ def test_corr_loss_bf16_channels_last_feats_and_padded_code(cuda_dev):
     gg = torch.autograd.grad(tot, [cg, cpg])
     assert _rel(gg[0], gw[0]) < 1e-4
     assert _rel(gg[1], gw[1]) < 1e-4
+
+
+@pytest.mark.parametrize("B,E,h,w,fs,neg", [(1, 384, 14, 14, 11, 5), (2, 128, 9, 13, 5, 2), (3, 64, 7, 5, 3, 0),
+                                             (4, 384, 28, 20, 11, 1)])
+def test_corr_loss_edge_shapes(cuda_dev, B, E, h, w, fs, neg):
+    """Edge cases: batch of one (super_perm(1) == [0]: the negative of an image is itself), non-square maps,
+    fewer sample points / negatives than the shipped config, no negatives at all."""
+    import stego_oracle as O
+    from stego_b200 import corr
+    D = 70
+    cfg = O.LossCfg(feature_samples=fs, neg_samples=neg)
+    g = torch.Generator().manual_seed(B * 31 + h)
+    feats, feats_pos = torch.randn(B, E, h, w, generator=g), torch.randn(B, E, h, w, generator=g)
+    code = torch.randn(B, D, h, w, generator=g, requires_grad=True)
+    code_pos = torch.randn(B, D, h, w, generator=g, requires_grad=True)
+    torch.manual_seed(B)
+    c1, c2, perms = O.draw_loss_randomness(B, cfg)
+    c1 = c1 * 1.2  # some coordinates outside [-1, 1]: border clamping
+    want = O.correlation_loss(feats, feats_pos, code, code_pos, c1, c2, perms, cfg) if neg > 0 else None
+    if neg == 0:
+        f, c = O.bilinear_sample(feats, c1), O.bilinear_sample(code, c1)
+        fp, cp = O.bilinear_sample(feats_pos, c2), O.bilinear_sample(code_pos, c2)
+        li, _ = O.corr_helper(f, f, c, c, cfg.pos_intra_shift, cfg)
+        le, _ = O.corr_helper(f, fp, c, cp, cfg.pos_inter_shift, cfg)
+        wl = 0.67 * li.mean() + 0.25 * le.mean()
+        want_losses = [li.mean(), le.mean()]
+    else:
+        wl = O.weighted_correspondence_loss(want, cfg)
+        want_losses = [want[0], want[2]] + [x.mean() for x in want[4].chunk(neg, 0)]
+    gw = torch.autograd.grad(wl, [code, code_pos])
+    spec = corr.LossSpec(cfg)
+    dc = lambda t: t.detach().to(cuda_dev)
+    cg, cpg = dc(code).requires_grad_(True), dc(code_pos).requires_grad_(True)
+    losses, _, _, _ = corr.corr_loss(dc(feats), dc(feats_pos), cg, cpg, dc(c1), dc(c2), [dc(p) for p in perms], spec)
+    assert losses.shape == (2 + neg,)
+    for got, ref in zip(losses.tolist(), want_losses):
+        assert abs(got - ref.item()) < 2e-5 + 1e-4 * abs(ref.item())
+    tot = 0.67 * losses[0] + 0.25 * losses[1] + (0.63 * losses[2:].mean() if neg > 0 else 0.0)
+    gg = torch.autograd.grad(tot, [cg, cpg])
+    assert _rel(gg[0], gw[0]) < 2e-4
+    assert _rel(gg[1], gw[1]) < 2e-4
+
+
+def test_corr_loss_rejects_unsupported(cuda_dev):
+    from stego_b200 import corr
+    from stego_b200.config import make_cfg
+    with pytest.raises(RuntimeError, match="feature_samples"):
+        corr.LossSpec(make_cfg(feature_samples=12))
+    spec = corr.LossSpec(make_cfg())
+    f = torch.randn(2, 100, 8, 8, device=cuda_dev)  # channels not a multiple of 64
+    c = torch.randn(2, 70, 8, 8, device=cuda_dev)
+    z = torch.zeros(2, 11, 11, 2, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        corr.corr_loss(f, f, c, c, z, z, [torch.zeros(2, dtype=torch.long, device=cuda_dev)] * 5, spec)
