@@ -39,5 +39,20 @@ if "attn" in which:
     ao = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
     for _ in range(2):
         ops.attention(qkv, ao, B2, N, E, heads)
+if "corr" in which:
+    from stego_b200 import corr
+    from stego_b200.config import make_cfg
+    spec = corr.LossSpec(make_cfg())
+    Bq, h = 32, 28
+    feats = torch.randn(Bq, h, h, E, device=dev).bfloat16().permute(0, 3, 1, 2)
+    feats_pos = torch.randn(Bq, h, h, E, device=dev).bfloat16().permute(0, 3, 1, 2)
+    code = torch.randn(Bq, h, h, 72, device=dev)[..., :70].permute(0, 3, 1, 2).requires_grad_(True)
+    code_pos = torch.randn(Bq, h, h, 72, device=dev)[..., :70].permute(0, 3, 1, 2).requires_grad_(True)
+    c1 = torch.rand(Bq, 11, 11, 2, device=dev) * 2 - 1
+    c2 = torch.rand(Bq, 11, 11, 2, device=dev) * 2 - 1
+    perms = torch.stack([torch.randperm(Bq, device=dev) for _ in range(5)])
+    for _ in range(2):
+        losses, _, _, _ = corr.corr_loss(feats, feats_pos, code, code_pos, c1, c2, perms, spec)
+        losses.sum().backward()
 torch.cuda.synchronize()
 print("done")
