@@ -74,32 +74,33 @@ __device__ __forceinline__ float gelu_erf_poly(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
-// Eight elements in lock-step: the Horner chain is 10 dependent FMAs (4-cycle latency each); evaluated element by
-// element two epilogue warps per scheduler could only issue every 4th cycle (measured: issue slots 51 % busy).
-// Coefficient-outer / element-inner order gives the scheduler 8 independent chains per warp.
+// bf16-output GELU, eight elements in lock-step (independent FMA chains), 13 instructions per element:
+//   erf(|x|/sqrt2) = xc * Q(xc^2), xc = min(|x|, 3.2*sqrt2), Q of degree 8 (minimax fit, |abs err| < 4.3e-5 in
+//   fp32 evaluation — two orders of magnitude below the bf16 rounding of the result), and
+//   gelu(x) = 0.5 x (1 + sign(x) erf(|x|/sqrt2)) = h + |h| * e with h = x/2.
 __device__ __forceinline__ void gelu_erf_poly8(float* x) {
-  float z[8], t[8], p[8];
+  float xc[8], u[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    z[j] = fminf(fabsf(x[j]) * 0.70710678118654752f, 3.2f);
-    t[j] = z[j] * z[j];
-    p[j] = fmaf(t[j], -2.4003365851451727e-09f, 1.4192566410626377e-07f);
+    xc[j] = fminf(fabsf(x[j]), 4.525483399593904f);
+    u[j] = xc[j] * xc[j];
+    q[j] = fmaf(u[j], 7.28493733954992e-11f, -7.739619932988917e-09f);
   }
-#define STEGO_POLY_STEP(C)                   \
-  _Pragma("unroll") for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], t[j], C);
-  STEGO_POLY_STEP(-3.73997355423602e-06f)
-  STEGO_POLY_STEP(5.846926586228758e-05f)
-  STEGO_POLY_STEP(-0.0006113043563036988f)
-  STEGO_POLY_STEP(0.004584169635313263f)
-  STEGO_POLY_STEP(-0.025814482266624247f)
-  STEGO_POLY_STEP(0.11186436329524356f)
-  STEGO_POLY_STEP(-0.37570728585235524f)
-  STEGO_POLY_STEP(1.1283256165012454f)
+#define STEGO_POLY_STEP(C) \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], u[j], C);
+  STEGO_POLY_STEP(3.6041332307651457e-07f)
+  STEGO_POLY_STEP(-9.764514095986007e-06f)
+  STEGO_POLY_STEP(0.0001730121070631224f)
+  STEGO_POLY_STEP(-0.0021448454598048446f)
+  STEGO_POLY_STEP(0.01943352726774955f)
+  STEGO_POLY_STEP(-0.13244709440462024f)
+  STEGO_POLY_STEP(0.7977185244870058f)
 #undef STEGO_POLY_STEP
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float e = fminf(p[j] * z[j], 1.0f);
-    x[j] = 0.5f * x[j] * (1.0f + copysignf(e, x[j]));
+    const float e = q[j] * xc[j];
+    const float h = 0.5f * x[j];
+    x[j] = fmaf(fabsf(h), e, h);
   }
 }
 
