@@ -457,10 +457,18 @@ def main():
         step_ms = ms_dev / args.steps
         for k, v in ks.items():
             v["share_of_step"] = v["ms"] * v["launches_per_step"] / step_ms
-        dom = max((k for k in ks if "tflops" in ks[k] and k != "corr_loss_fwd"), key=lambda k: ks[k]["share_of_step"])
+        dom = max((k for k in ks if "tflops" in ks[k] and k != "corr_loss_fwd" and not k.startswith("diag_")),
+                  key=lambda k: ks[k]["share_of_step"])
         d = ks[dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("config") == args.config and not args.batch:
+                traffic = tj["bytes_per_launch"].get(dom)
         line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peaks["tf_burst"],
-                            "unit": "TFLOP/s", "frac": d["tflops"] / peaks["tf_burst"], "traffic": None,
+                            "unit": "TFLOP/s", "frac": d["tflops"] / peaks["tf_burst"], "traffic": traffic,
+                            "algorithmic_bytes_per_launch": d["bytes"],
                             "algorithmic_flops_per_launch": d["flops"], "ms_per_launch": d["ms"],
                             "share_of_step": d["share_of_step"], "peak_source": peaks["source"] + ", burst"}
         c = ks["corr_loss_fwd"]

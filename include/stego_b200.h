@@ -162,6 +162,21 @@ STEGO_API int stego_linear_probe_ce(const float* code, long long ld_code, int C,
                                     float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
                                     float* loss_out, float grad_loss, float* dW, float* db, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused evaluation probes (src/eval_segmentation.py:128-131, BASELINE.json configs[4]):
+ *   code_up = F.interpolate(code, (H, W), mode="bilinear", align_corners=False)
+ *   lin_log_probs = log_softmax(linear_probe(code_up), 1);  clu_log_probs = cluster_probe(code_up, alpha, log_probs=True)
+ * evaluated per output pixel from the LOW-RES code (the [B,C,H,W] upsampled tensor is never materialised).
+ *   code: tokens-major low-res code [B*h*w][ld_code] fp32; lin_weight [n_lin][C], lin_bias [n_lin], clusters [n_clu][C];
+ *   lr_scratch: [B*h*w][72] floats.  Outputs (each may be null): log-probabilities [B][n][H][W] fp32 and
+ *   per-pixel argmax maps [B][H][W] uint8.  C <= 96, n_lin, n_clu <= 32, H >= h, W >= w.
+ * ---------------------------------------------------------------------------------------------- */
+STEGO_API int stego_eval_probes(const float* code, long long ld_code, int C, int B, int h, int w, int H, int W,
+                                const float* lin_weight, const float* lin_bias, int n_lin, const float* clusters,
+                                int n_clu, float alpha, float* lr_scratch, float* lin_log_probs,
+                                float* clu_log_probs, unsigned char* lin_argmax, unsigned char* clu_argmax,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

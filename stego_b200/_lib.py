@@ -32,6 +32,7 @@ _CTYPES = {
     "const int*": ctypes.c_void_p,
     "int*": ctypes.c_void_p,
     "const char*": ctypes.c_char_p,
+    "unsigned char*": ctypes.c_void_p,
 }
 
 
