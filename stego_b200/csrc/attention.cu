@@ -242,25 +242,45 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         }
       }
       const float mc = m_run * c;
-      // p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem (8 keys = one 16-byte chunk at a time)
+      // p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem (8 keys = one 16-byte chunk at a time).
+      // Full tiles (all but the last) take the select-free path: a per-element mask costs an ISETP + FSEL each.
       float rs = 0.f;
+      if (valid >= ATT_BKV) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float e[8];
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const float x = ex2_approx(fmaf(__uint_as_float(v[h][8 * g + t]), c, -mc));
-            e[t] = (valid >= ATT_BKV || h * 32 + 8 * g + t < valid) ? x : 0.f;
+            for (int t = 0; t < 8; ++t) e[t] = ex2_approx(fmaf(__uint_as_float(v[h][8 * g + t]), c, -mc));
+            uint4 w;
+            w.x = pack_bf16x2(e[0], e[1]);
+            w.y = pack_bf16x2(e[2], e[3]);
+            w.z = pack_bf16x2(e[4], e[5]);
+            w.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(sp + sw128_offset(r, h * 4 + g)) = w;
+            rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
           }
-          uint4 w;
-          w.x = pack_bf16x2(e[0], e[1]);
-          w.y = pack_bf16x2(e[2], e[3]);
-          w.z = pack_bf16x2(e[4], e[5]);
-          w.w = pack_bf16x2(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sp + sw128_offset(r, h * 4 + g)) = w;
-          rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float x = ex2_approx(fmaf(__uint_as_float(v[h][8 * g + t]), c, -mc));
+              e[t] = (h * 32 + 8 * g + t < valid) ? x : 0.f;
+            }
+            uint4 w;
+            w.x = pack_bf16x2(e[0], e[1]);
+            w.y = pack_bf16x2(e[2], e[3]);
+            w.z = pack_bf16x2(e[4], e[5]);
+            w.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(sp + sw128_offset(r, h * 4 + g)) = w;
+            rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          }
         }
       }
       l_run += rs;
