@@ -104,13 +104,25 @@ class _CorrLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, code, code_pos, feats, feats_pos, coords1, coords2, perms, spec: LossSpec, want_elems: bool,
-                chan_scale, chan_scale_pos, raw_perms=False):
-        B, E, D, H, W, coords1, coords2, perms_t = _prep_common(feats, feats_pos, code, code_pos, coords1, coords2,
-                                                                 perms, spec)
-        code_f = code.detach()
-        if code_f.dtype != torch.float32:
-            code_f = code_f.float()
-        code_pos_f = _same_layout(code_f, code_pos.detach().to(torch.float32))
+                chan_scale, chan_scale_pos, raw_perms=False, pair=False):
+        # pair=True: `code` is the [2B, D, h, w] output of ONE head pass over img ++ img_pos (code_pos is None); its
+        # gradient is then produced in one buffer instead of two tensors that autograd has to re-assemble.
+        if pair:
+            half = code.shape[0] // 2
+            code_all = code.detach()
+            if code_all.dtype != torch.float32:
+                code_all = code_all.float()
+            code_f, code_pos_f = code_all[:half], code_all[half:]
+            B, E, D, H, W, coords1, coords2, perms_t = _prep_common(feats, feats_pos, code_f, code_pos_f, coords1,
+                                                                     coords2, perms, spec)
+        else:
+            B, E, D, H, W, coords1, coords2, perms_t = _prep_common(feats, feats_pos, code, code_pos, coords1, coords2,
+                                                                     perms, spec)
+            code_f = code.detach()
+            if code_f.dtype != torch.float32:
+                code_f = code_f.float()
+            code_pos_f = _same_layout(code_f, code_pos.detach().to(torch.float32))
+        ctx.pair = bool(pair)
         dev = code.device
         ftiles = build_tiles(feats.detach(), feats_pos.detach(), coords1, coords2, perms_t, spec, E, chan_scale,
                              chan_scale_pos, raw_perms)
@@ -132,7 +144,7 @@ class _CorrLossFn(torch.autograd.Function):
         _lib.check(rc, "stego_corr_loss_fwd")
         ctx.spec = spec
         ctx.dims = (B, E, D, H, W)
-        ctx.code_dtype = (code.dtype, code_pos.dtype)
+        ctx.code_dtype = (code.dtype, code_pos.dtype if code_pos is not None else code.dtype)
         ctx.save_for_backward(ftiles, ctiles, stats, code_f, code_pos_f, coords1, coords2,
                               perms_t if perms_t is not None else torch.empty(0, device=dev))
         losses = stats[:, 0].clone()
@@ -159,8 +171,14 @@ class _CorrLossFn(torch.autograd.Function):
             int(spec.pointwise), int(spec.zero_clamp), int(spec.stabilize), _lib.ptr(stats), _lib.ptr(gscale),
             _lib.ptr(gel), _lib.ptr(gcd), _lib.ptr(dtiles), _lib.stream())
         _lib.check(rc, "stego_corr_loss_bwd")
-        dcode = _zeros_strided_like(code_f)
-        dcode_pos = _zeros_strided_like(code_f)
+        if ctx.pair:
+            # code_f / code_pos_f are the two halves of one tensor: one zero-filled buffer with its layout
+            full_size = (2 * B,) + tuple(code_f.shape[1:])
+            dall = _zeros_strided_like(torch.as_strided(code_f, full_size, code_f.stride()))
+            dcode, dcode_pos = dall[:B], dall[B:]
+        else:
+            dcode = _zeros_strided_like(code_f)
+            dcode_pos = _zeros_strided_like(code_f)
         sb, sc, sy, sx = code_f.stride()
         rc = _lib.load().stego_sample_norm_bwd(
             _lib.ptr(code_f), _lib.ptr(code_pos_f), sb, sc, sy, sx, _lib.ptr(coords1), _lib.ptr(coords2),
@@ -168,14 +186,17 @@ class _CorrLossFn(torch.autograd.Function):
             spec.nslots, int(ctx.raw_perms), _lib.stream())
         _lib.check(rc, "stego_sample_norm_bwd")
         d0, d1 = ctx.code_dtype
-        return (dcode.to(d0), dcode_pos.to(d1), None, None, None, None, None, None, None, None, None, None)
+        if ctx.pair:
+            return (dall.to(d0), None) + (None,) * 11
+        return (dcode.to(d0), dcode_pos.to(d1)) + (None,) * 11
 
 
 def corr_loss(feats, feats_pos, code, code_pos, coords1, coords2, perms, spec: LossSpec, want_elems: bool = False,
-              chan_scale=None, chan_scale_pos=None, raw_perms: bool = False):
+              chan_scale=None, chan_scale_pos=None, raw_perms: bool = False, pair: bool = False):
     """raw_perms=True: `perms` holds the raw torch.randperm draws and the sampling kernel applies super_perm's
     fix-up itself (saves the eq/add/remainder launches of modules.super_perm).
+    pair=True: `code` holds code ++ code_pos ([2B, D, h, w], one head pass) and `code_pos` is None.
     Returns (losses[ncalls], cd_means[ncalls], cd[ncalls,B,S,S]|None, loss_elems|None).
     losses[k] is the mean of helper call k (0 intra, 1 inter, 2.. negatives); differentiable wrt code/code_pos."""
     return _CorrLossFn.apply(code, code_pos, feats, feats_pos, coords1, coords2, perms, spec, want_elems,
-                             chan_scale, chan_scale_pos, raw_perms)
+                             chan_scale, chan_scale_pos, raw_perms, pair)

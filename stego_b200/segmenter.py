@@ -274,9 +274,10 @@ class LitUnsupervisedSegmenter(nn.Module):
             for i in range(cfg.neg_samples):
                 torch.randperm(B, device=img.device, dtype=torch.long, out=perms[i])
             # the returned-feature dropout (modules.py:116) is folded into the sampling kernel (chan_scale)
-            losses, cd_means, _, _ = corr.corr_loss(feats, feats_pos, code, code_pos, coords1, coords2, perms, self._spec,
+            losses, cd_means, _, _ = corr.corr_loss(feats, feats_pos, code_all, None, coords1, coords2, perms, self._spec,
                                                     want_elems=False, chan_scale=m3 if cfg.dropout else None,
-                                                    chan_scale_pos=p3 if cfg.dropout else None, raw_perms=True)
+                                                    chan_scale_pos=p3 if cfg.dropout else None, raw_perms=True,
+                                                    pair=True)
             pos_intra_loss, pos_inter_loss = losses[0], losses[1]
             neg_inter_loss = losses[2:].mean()
             self.log('loss/pos_intra', pos_intra_loss)
