@@ -53,4 +53,8 @@ def test_fused_eval_probes_full_frame_properties(cuda_dev):
     assert l.shape == (1, 27, 1024, 2048)
     assert (l.exp().sum(1) - 1).abs().max().item() < 1e-4
     assert (c.exp().sum(1) - 1).abs().max().item() < 1e-4
-    assert torch.equal(l.argmax(1), la.long()) and torch.equal(c.argmax(1), ca.long())
+    # the kernel's argmax attains the maximum log-probability (indices may differ from torch.argmax only where two
+    # classes round to the same fp32 log-prob)
+    assert torch.equal(l.gather(1, la.long().unsqueeze(1)).squeeze(1), l.max(1).values)
+    assert torch.equal(c.gather(1, ca.long().unsqueeze(1)).squeeze(1), c.max(1).values)
+    assert (l.argmax(1) != la.long()).float().mean().item() < 1e-4
