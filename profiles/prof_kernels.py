@@ -54,5 +54,13 @@ if "corr" in which:
     for _ in range(2):
         losses, _, _, _ = corr.corr_loss(feats, feats_pos, code, code_pos, c1, c2, perms, spec)
         losses.sum().backward()
+if "ce" in which:
+    from stego_b200.segmenter import linear_probe_ce
+    code = torch.randn(32, 28, 28, 72, device=dev)[..., :70].permute(0, 3, 1, 2)
+    w = (torch.randn(27, 70, 1, 1, device=dev) * 0.3).requires_grad_(True)
+    b = torch.zeros(27, device=dev, requires_grad=True)
+    label = torch.randint(-1, 27, (32, 224, 224), device=dev)
+    for _ in range(2):
+        linear_probe_ce(code, w, b, label).backward()
 torch.cuda.synchronize()
 print("done")

@@ -189,8 +189,8 @@ eval_probe_kernel(EvalProbeParams p) {
       float se = 0.f;
 #pragma unroll
       for (int k = 0; k < 32; ++k)
-        if (k < p.n_lin) se += expf(z[k] - mx);
-      const float lse = mx + logf(se);
+        if (k < p.n_lin) se += __expf(z[k] - mx);
+      const float lse = mx + __logf(se);
       float* o = p.lin_logp + (1ll * b * p.n_lin) * plane + pix;
 #pragma unroll
       for (int k = 0; k < 32; ++k)
@@ -223,8 +223,8 @@ eval_probe_kernel(EvalProbeParams p) {
       float se = 0.f;
 #pragma unroll
       for (int k = 0; k < 32; ++k)
-        if (k < p.n_clu) se += expf(z[k] * p.alpha - m2);
-      const float lse = m2 + logf(se);
+        if (k < p.n_clu) se += __expf(z[k] * p.alpha - m2);
+      const float lse = m2 + __logf(se);
       float* o = p.clu_logp + (1ll * b * p.n_clu) * plane + pix;
 #pragma unroll
       for (int k = 0; k < 32; ++k)

@@ -77,31 +77,47 @@ relu_bwd_kernel(const float* __restrict__ dh, const bf16* __restrict__ h, bf16* 
   reinterpret_cast<uint2*>(out)[idx] = w;
 }
 
-// out[c] += sum over rows of in[row][c].  One warp per 32-row chunk, lanes stride over the columns (coalesced
-// row reads), block-level combine in shared memory, one atomic per (block, column).
-template <typename T, int NV>  // NV = ceil(C / 32)
+// out[c] += sum over rows of in[row][c].  One warp per 32-row chunk; each lane owns 16-byte column groups
+// (8 bf16 / 4 fp32) so a row is read with full-width coalesced loads; block-level combine in shared memory, one
+// atomic per (block, column).  Requires ld * sizeof(T) % 16 == 0 and a 16-byte aligned base (checked on the host).
+template <typename T, int NG>  // NG = ceil(C / (32 * V)), V = 16 / sizeof(T)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, int ld, int C, long long rows, float* __restrict__ out) {
-  __shared__ float part[8][NV * 32];
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float part[8][NG * 32 * V];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r0 = (1ll * blockIdx.x * 8 + warp) * 32;
-  float acc[NV];
+  float acc[NG][V];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
   for (long long r = r0; r < r0 + 32 && r < rows; ++r) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = lane + 32 * k;
-      if (c < C) {
-        if constexpr (sizeof(T) == 2)
-          acc[k] += __bfloat162float(in[r * ld + c]);
-        else
-          acc[k] += in[r * ld + c];
+    for (int g = 0; g < NG; ++g) {
+      const int c = (lane + 32 * g) * V;
+      if (c < C) {  // C % V == 0 is guaranteed by the host for this path
+        const uint4 raw = *reinterpret_cast<const uint4*>(in + r * ld + c);
+        if constexpr (sizeof(T) == 2) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float2 f = __bfloat1622float2(h[v]);
+            acc[g][2 * v] += f.x;
+            acc[g][2 * v + 1] += f.y;
+          }
+        } else {
+          const float* f = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[g][v] += f[v];
+        }
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < NV; ++k) part[warp][lane + 32 * k] = acc[k];
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) part[warp][(lane + 32 * g) * V + v] = acc[g][v];
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = 0.f;
@@ -109,6 +125,22 @@ colsum_kernel(const T* __restrict__ in, int ld, int C, long long rows, float* __
     for (int w = 0; w < 8; ++w) t += part[w][c];
     atomicAdd(out + c, t);
   }
+}
+
+// scalar fallback (any C / alignment): one thread per column, row chunk per blockIdx.y
+template <typename T>
+__global__ void __launch_bounds__(128)
+colsum_scalar_kernel(const T* __restrict__ in, int ld, int C, long long rows, int rows_per_block, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = 1ll * blockIdx.y * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    if constexpr (sizeof(T) == 2) acc += __bfloat162float(in[r * ld + c]);
+    else acc += in[r * ld + c];
+  }
+  atomicAdd(out + c, acc);
 }
 
 // torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False): step is 1-based.
@@ -170,17 +202,32 @@ extern "C" int stego_relu_bwd_bf16(const float* dh, const void* h_bf16, void* ou
 extern "C" int stego_colsum(const void* in, int in_is_bf16, int ld, int C, long long rows, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(in && out && C > 0 && C <= ld && rows > 0, "stego_colsum: bad args");
-  const unsigned blocks = (unsigned)((rows + 255) / 256);
-  const int nv = (C + 31) / 32;
-#define STEGO_COLSUM(T, NV) colsum_kernel<T, NV><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(in), ld, C, rows, out)
-  if (in_is_bf16) {
-    if (nv <= 3) STEGO_COLSUM(bf16, 3); else if (nv <= 12) STEGO_COLSUM(bf16, 12); else if (nv <= 24) STEGO_COLSUM(bf16, 24);
-    else { set_error("stego_colsum: C=%d unsupported (<= 768)", C); return STEGO_ERR_UNSUPPORTED; }
+  const size_t esz = in_is_bf16 ? 2 : 4;
+  const int V = (int)(16 / esz);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (size_t(ld) * esz) % 16 == 0 && C % V == 0 &&
+                      C <= (in_is_bf16 ? 768 : 384);
+  if (vec_ok) {
+    const unsigned blocks = (unsigned)((rows + 255) / 256);
+    const int ng = (C + 32 * V - 1) / (32 * V);
+    if (in_is_bf16) {
+      const bf16* p = reinterpret_cast<const bf16*>(in);
+      if (ng <= 1) colsum_kernel<bf16, 1><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+      else if (ng <= 2) colsum_kernel<bf16, 2><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+      else colsum_kernel<bf16, 3><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+    } else {
+      const float* p = reinterpret_cast<const float*>(in);
+      if (ng <= 1) colsum_kernel<float, 1><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+      else if (ng <= 2) colsum_kernel<float, 2><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+      else colsum_kernel<float, 3><<<blocks, 256, 0, stream>>>(p, ld, C, rows, out);
+    }
   } else {
-    if (nv <= 3) STEGO_COLSUM(float, 3); else if (nv <= 12) STEGO_COLSUM(float, 12); else if (nv <= 24) STEGO_COLSUM(float, 24);
-    else { set_error("stego_colsum: C=%d unsupported (<= 768)", C); return STEGO_ERR_UNSUPPORTED; }
+    const int rpb = 512;
+    dim3 grid((C + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+    if (in_is_bf16)
+      colsum_scalar_kernel<bf16><<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(in), ld, C, rows, rpb, out);
+    else
+      colsum_scalar_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(in), ld, C, rows, rpb, out);
   }
-#undef STEGO_COLSUM
   STEGO_CHECK_LAUNCH("colsum_kernel");
   return STEGO_OK;
 }

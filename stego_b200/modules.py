@@ -175,8 +175,11 @@ class _HeadFn(torch.autograd.Function):
         def splits_for(out_rows, out_cols):
             tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
             return max(1, min(64, M // 512, -(-296 // tiles)))  # ~2 CTAs per SM, bounded atomic fan-in
-        db = torch.zeros(D, dtype=torch.float32, device=dev)
-        _lib.check(lib.stego_colsum(_lib.ptr(dcode), 0, dcode.stride(0), D, M, _lib.ptr(db), _lib.stream()), "stego_colsum")
+        # bias gradient: column sums over the padded row (padding columns of d(code) are zero) -> vector loads
+        db_pad = torch.zeros(P, dtype=torch.float32, device=dev)
+        _lib.check(lib.stego_colsum(_lib.ptr(dcode), 0, dcode.stride(0), P if dcode.shape[1] >= P else D, M,
+                                    _lib.ptr(db_pad), _lib.stream()), "stego_colsum")
+        db = db_pad[:D].contiguous()
         dw1 = torch.zeros(D, E, dtype=torch.float32, device=dev)
         ops.gemm(dyb, x1, dw1, M=D, N=E, K=M, a_mn=True, b_mn=True, splits=splits_for(D, E), atomic=True)
         dwa = dba = dwb = dbb = None
