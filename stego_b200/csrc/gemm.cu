@@ -13,6 +13,8 @@
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM, 2 buffers)
 //   warps 2..9  epilogue       (tcgen05.ld TMEM->regs, bias/GELU/ReLU/residual, smem transpose, coalesced stores)
 // Operand tiles are 128 x 64 (A) and BN x 64 (B) bf16; accumulation fp32.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -104,7 +106,7 @@ __device__ __forceinline__ void gelu_erf_poly8(float* x) {
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, GemmParams p) {
@@ -122,6 +124,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, N0, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
   constexpr uint32_t IDESC_TAIL = make_idesc_bf16(GEMM_BM, 128, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
   static_assert(BN != 384 || (!A_MN && !B_MN), "384-wide tiles are K-major only");
+  // kCluster: two CTAs (a thread-block cluster) work on two M-adjacent tiles of the same N block; each loads its own
+  // A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> B traffic from L2 is halved.
+  static_assert(!kCluster || (!A_MN && !B_MN && BN != 384), "cluster multicast: K-major 128/256 tiles only");
+  constexpr uint32_t B_BOX_ROWS = kCluster ? (BN / 2) : 128;  // rows of one B TMA box (tensor map built to match)
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -136,10 +143,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_m_real = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_m = kCluster ? ((tiles_m_real + 1) & ~1) : tiles_m_real;  // cluster: pairs of M tiles (last may be OOB)
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;  // K tail: TMA zero-fills out-of-bounds
-  const int total_tiles = tiles_m * tiles_n * p.splits;
+  // cluster mode: the scheduler walks PAIRS; both CTAs of a cluster see the same pair sequence
+  const int total_tiles = kCluster ? (tiles_m / 2) * tiles_n : tiles_m * tiles_n * p.splits;
+  const int sched_start = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int sched_step = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -147,7 +158,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tma_epi) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCluster ? 2 : 1);  // cluster: both CTAs' MMAs must release a stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -158,6 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -165,10 +177,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = t % p.splits;
-        const int tn = (t / p.splits) % tiles_n;
-        const int tm = t / (p.splits * tiles_n);
+      for (int t = sched_start; t < total_tiles; t += sched_step) {
+        const int split = kCluster ? 0 : t % p.splits;
+        const int tn = kCluster ? t % tiles_n : (t / p.splits) % tiles_n;
+        const int tm = kCluster ? (t / tiles_n) * 2 + static_cast<int>(crank) : t / (p.splits * tiles_n);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -183,7 +195,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int blk = 0; blk < GEMM_BM / 64; ++blk)
               tma_load_2d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK);
           }
-          if (!B_MN) {
+          if (kCluster) {
+            // this CTA's half of the B tile, delivered to both CTAs (and counted on both full barriers)
+            tma_load_2d_multicast(sb + crank * (B_BOX_ROWS * 128), &tmB, &full_bar[stage], kb * GEMM_BK,
+                                  tn * BN + crank * B_BOX_ROWS, 0x3);
+          } else if (!B_MN) {
 #pragma unroll
             for (int blk = 0; blk < BN / 128; ++blk)  // tensor-map box = 128 rows
               tma_load_2d(sb + blk * 16384, &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * 128);
@@ -201,8 +217,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = t % p.splits;
+      for (int t = sched_start; t < total_tiles; t += sched_step) {
+        const int split = kCluster ? 0 : t % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -226,7 +242,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_bf16(tmem_d + 256, da, make_smem_desc_sw128(sb + 256 * 128 + k * 32, 16, 1024), IDESC_TAIL,
                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kCluster) umma_commit_multicast(&empty_bar[stage], 0x3);  // release the stage in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -239,9 +256,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate column groups
     uint32_t acc = 0, acc_phase = 0;
     uint32_t epi_groups = 0;  // bulk-store groups this warp has committed (selects the staging tile)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int tn = (t / p.splits) % tiles_n;
-      const int tm = t / (p.splits * tiles_n);
+    for (int t = sched_start; t < total_tiles; t += sched_step) {
+      const int tn = kCluster ? t % tiles_n : (t / p.splits) % tiles_n;
+      const int tm = kCluster ? (t / tiles_n) * 2 + static_cast<int>(crank) : t / (p.splits * tiles_n);
       if (p.fast_epi && !p.tma_epi && p.residual != nullptr) {
         // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
         const int prow = tm * GEMM_BM + quarter * 32 + lane;
@@ -573,24 +590,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (p.tma_epi && warp >= 2 && lane == 0) tma_wait_group_read<0>();  // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // neither CTA may exit while the peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        cudaStream_t stream) {
   constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * (BN == 384 ? 1 : 2) * 4096 + 1024 + 256;
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, kCluster>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * p.splits;
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  if (kCluster) {
+    const int pairs = ((tiles_m + 1) / 2) * tiles_n;
+    int clusters = num_sms() / 2;
+    if (pairs < clusters) clusters = pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm cluster)");
+    count_launch();
+    return STEGO_OK;
+  }
+  const int tiles = tiles_m * tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p);
   STEGO_CHECK_LAUNCH("gemm_bf16_kernel launch");
@@ -635,6 +676,14 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
                !(out_bf16 && residual != nullptr);
   // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
   const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
+  // 2-CTA clusters with TMA multicast of the shared B tile (K-major, no split-K, enough M tiles to pair up)
+  static int cluster_opt = -1;
+  if (cluster_opt < 0) {
+    const char* e = getenv("STEGO_GEMM_CLUSTER");
+    cluster_opt = e ? atoi(e) : 0;
+  }
+  const bool use_384 = !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
+  const bool cluster = cluster_opt && !a_mn_major && !b_mn_major && splits == 1 && !atomic_out && M >= 512 && !use_384;
 
   // TMA epilogue: plain store for outputs without a residual; fp32 reduce-add when the residual IS the output
   // (the in-place x += ... of the transformer blocks) — then the epilogue issues no global loads at all.
@@ -656,7 +705,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   {
     uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, b_mn_major ? 64u : 128u};
+    uint32_t box[2] = {64, b_mn_major ? 64u : ((cluster && !wide) ? 64u : 128u)};
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
   if (p.tma_epi) {
@@ -670,8 +719,11 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   }
   // N == 384 (ViT-S proj / fc2, in-place residual): one 128 x 384 tile per CTA reads each A row block once
   // (only worth it when the mainloop dominates: the single accumulator cannot overlap epilogue and MMAs)
-  if (p.tma_epi && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1)
-    return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
+  if (p.tma_epi && use_384) return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
+  if (cluster && !(p.tma_epi == 0 && use_384)) {
+    if (wide) return launch_gemm<256, 3, false, false, true>(tmA, tmB, tmO, p, stream);
+    return launch_gemm<128, 5, false, false, true>(tmA, tmB, tmO, p, stream);
+  }
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);

@@ -328,12 +328,14 @@ constexpr int LCE_TILE = 16;  // hi-res pixels per tile side (256 threads = one 
 //   2. the bilinear transpose is separable: T[Y][cx][k] = sum_X wx[X][cx] g[Y][X][k], then
 //      G[cy][cx][k] = sum_Y wy[Y][cy] T[Y][cx][k], each a conflict-free shared-memory reduction.
 //   3. one global atomic per (box cell, class) of the tile.
+constexpr int LCE_SLD = 33;  // smem stride of one box cell (odd: lanes reading different cells hit different banks)
+
 __global__ void __launch_bounds__(256)
 linear_ce_kernel(LinearCEParams p) {
   extern __shared__ float sm[];
   const int bhm = p.box_h, bwm = p.box_w, n = p.n;
-  float* slog = sm;                                   // [box_h*box_w][LP_LD]
-  float* sg = slog + bhm * bwm * LP_LD;               // [256][n]   (odd stride n=27: conflict-free)
+  float* slog = sm;                                   // [box_h*box_w][LCE_SLD]
+  float* sg = slog + bhm * bwm * LCE_SLD;             // [256][n]   (odd stride n=27: conflict-free)
   float* sT = sg + 256 * n;                           // [16][box_w][n]
   float* swx = sT + LCE_TILE * bwm * n;               // [16][box_w]
   float* swy = swx + LCE_TILE * bwm;                  // [16][box_h]
@@ -354,10 +356,11 @@ linear_ce_kernel(LinearCEParams p) {
   const int bh = by1 - by0 + 1, bw = bx1 - bx0 + 1;  // <= box_h, box_w by construction on the host
   const long long base = 1ll * b * p.h * p.w;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < bh * bw * LP_LD; idx += 256) {
-    const int k = idx % LP_LD, cell = idx / LP_LD;
-    const int r = cell / bw, c = cell % bw;
-    slog[idx] = (k < n) ? p.logits[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + k] : 0.f;
+  const int warp = tid >> 5, lane = tid & 31;
+  // box load: one warp per cell, lanes = classes (no integer division in the loop)
+  for (int cell = warp; cell < bh * bw; cell += 8) {
+    const int r = cell / bw, c = cell - r * bw;
+    slog[cell * LCE_SLD + lane] = (lane < n) ? p.logits[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LP_LD + lane] : 0.f;
   }
   for (int idx = tid; idx < LCE_TILE * bwm; idx += 256) swx[idx] = 0.f;
   for (int idx = tid; idx < LCE_TILE * bhm; idx += 256) swy[idx] = 0.f;
@@ -391,14 +394,16 @@ linear_ce_kernel(LinearCEParams p) {
     src_index(min(Y, p.H - 1), sy, p.h, y0, y1, ly);
     src_index(min(X, p.W - 1), sx, p.w, x0, x1, lx);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const int c00 = ((y0 - by0) * bw + (x0 - bx0)) * LP_LD, c01 = ((y0 - by0) * bw + (x1 - bx0)) * LP_LD;
-    const int c10 = ((y1 - by0) * bw + (x0 - bx0)) * LP_LD, c11 = ((y1 - by0) * bw + (x1 - bx0)) * LP_LD;
+    const float* l00 = slog + ((y0 - by0) * bw + (x0 - bx0)) * LCE_SLD;
+    const float* l01 = slog + ((y0 - by0) * bw + (x1 - bx0)) * LCE_SLD;
+    const float* l10 = slog + ((y1 - by0) * bw + (x0 - bx0)) * LCE_SLD;
+    const float* l11 = slog + ((y1 - by0) * bw + (x1 - bx0)) * LCE_SLD;
     float z[LP_LD];
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < LP_LD; ++k) {
       if (k < n) {
-        z[k] = w00 * slog[c00 + k] + w01 * slog[c01 + k] + w10 * slog[c10 + k] + w11 * slog[c11 + k];
+        z[k] = w00 * l00[k] + w01 * l01[k] + w10 * l10[k] + w11 * l11[k];
         mx = fmaxf(mx, z[k]);
       }
     }
@@ -408,22 +413,28 @@ linear_ce_kernel(LinearCEParams p) {
       if (k < n) { z[k] = __expf(z[k] - mx); se += z[k]; }   // z now holds exp(z - max)  (ex2.approx: 2 ulp)
     const float inv = 1.0f / se;
     if (valid) {
-      float el = 1.f;
-#pragma unroll
-      for (int k = 0; k < LP_LD; ++k)
-        if (k == lab) el = z[k];
-      lsum = -__logf(el * inv);  // lse - z_lab
+      const int li = static_cast<int>(lab);
+      const float zl = w00 * l00[li] + w01 * l01[li] + w10 * l10[li] + w11 * l11[li];  // dynamic smem index
+      lsum = __logf(se) - (zl - mx);  // lse - z_lab
       cnt = 1.f;
     }
     if (p.dlogits) {
+      float* gp = sg + tid * n;
+      if (valid) {
 #pragma unroll
-      for (int k = 0; k < LP_LD; ++k)
-        if (k < n) sg[tid * n + k] = valid ? (z[k] * inv - ((k == lab) ? 1.f : 0.f)) : 0.f;
+        for (int k = 0; k < LP_LD; ++k)
+          if (k < n) gp[k] = z[k] * inv;
+        gp[static_cast<int>(lab)] -= 1.f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < LP_LD; ++k)
+          if (k < n) gp[k] = 0.f;
+      }
     }
   }
   lsum = warp_sum(lsum);
   cnt = warp_sum(cnt);
-  if ((tid & 31) == 0) { sred[0][tid >> 5] = lsum; sred[1][tid >> 5] = cnt; }
+  if (lane == 0) { sred[0][warp] = lsum; sred[1][warp] = cnt; }
   __syncthreads();
   if (tid == 0) {
     double a = 0, c = 0;
@@ -431,22 +442,34 @@ linear_ce_kernel(LinearCEParams p) {
     if (c > 0) { atomicAdd(p.acc, a); atomicAdd(p.acc + 1, c); }
   }
   if (!p.dlogits) return;
-  // ---- phase 2a: reduce over the tile's columns
-  for (int o = tid; o < LCE_TILE * bw * n; o += 256) {
-    const int k = o % n, cx = (o / n) % bw, yy = o / (n * bw);
-    float acc = 0.f;
+  // ---- phase 2a: reduce over the tile's columns.  pair = (box column, class); each thread keeps ONE pair for all
+  //      the rows it handles, so the only integer division happens once per thread.
+  const int pairs = bw * n;                 // <= 160 for the shipped shapes
+  const int reps = max(1, 256 / pairs);     // row interleave factor
+  const int pair = tid % pairs, rep = tid / pairs;
+  const int pcx = pair / n, pk = pair - pcx * n;
+  if (rep < reps) {
+    for (int pr = pair; pr < pairs; pr += 256) {  // pairs > 256 only for very small upsampling ratios
+      const int cx = (pr == pair) ? pcx : pr / n, k = (pr == pair) ? pk : pr % n;
+      for (int yy = rep; yy < LCE_TILE; yy += reps) {
+        float acc = 0.f;
 #pragma unroll
-    for (int xx = 0; xx < LCE_TILE; ++xx) acc = fmaf(swx[xx * bwm + cx], sg[(yy * LCE_TILE + xx) * n + k], acc);
-    sT[(yy * bwm + cx) * n + k] = acc;
+        for (int xx = 0; xx < LCE_TILE; ++xx) acc = fmaf(swx[xx * bwm + cx], sg[(yy * LCE_TILE + xx) * n + k], acc);
+        sT[(yy * bwm + cx) * n + k] = acc;
+      }
+    }
   }
   __syncthreads();
   // ---- phase 2b + 3: reduce over the rows, one atomic per (cell, class)
-  for (int o = tid; o < bh * bw * n; o += 256) {
-    const int k = o % n, cx = (o / n) % bw, cy = o / (n * bw);
-    float acc = 0.f;
+  for (int cy = rep; cy < bh; cy += reps) {
+    if (rep >= reps) break;
+    for (int pr = pair; pr < pairs; pr += 256) {
+      const int cx = (pr == pair) ? pcx : pr / n, k = (pr == pair) ? pk : pr % n;
+      float acc = 0.f;
 #pragma unroll
-    for (int yy = 0; yy < LCE_TILE; ++yy) acc = fmaf(swy[yy * bhm + cy], sT[(yy * bwm + cx) * n + k], acc);
-    if (acc != 0.f) atomicAdd(p.dlogits + (base + 1ll * (by0 + cy) * p.w + bx0 + cx) * LP_LD + k, acc);
+      for (int yy = 0; yy < LCE_TILE; ++yy) acc = fmaf(swy[yy * bhm + cy], sT[(yy * bwm + cx) * n + k], acc);
+      if (acc != 0.f) atomicAdd(p.dlogits + (base + 1ll * (by0 + cy) * p.w + bx0 + cx) * LP_LD + k, acc);
+    }
   }
 }
 
@@ -612,7 +635,7 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   p.box_w = (int)((double)LCE_TILE * w / Wimg) + 3;
   if (p.box_h > h) p.box_h = h;
   if (p.box_w > w) p.box_w = w;
-  const size_t ce_smem = ((size_t)p.box_h * p.box_w * LP_LD + 256 * (size_t)n_classes + (size_t)LCE_TILE * p.box_w * n_classes +
+  const size_t ce_smem = ((size_t)p.box_h * p.box_w * LCE_SLD + 256 * (size_t)n_classes + (size_t)LCE_TILE * p.box_w * n_classes +
                           (size_t)LCE_TILE * (p.box_w + p.box_h)) * sizeof(float);
   STEGO_CHECK_ARG(ce_smem <= 200 * 1024, "stego_linear_probe_ce: upsample ratio %dx%d -> %dx%d needs %zu B of smem", h, w, H, Wimg, ce_smem);
   {
