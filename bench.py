@@ -380,6 +380,7 @@ def run_c4(args, rank, world, local):
         sampler.start()
     l0 = _lib.launch_count()
     ms_dev = run(args.steps, False)
+    host_enqueue_ms = host_ms[0]
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)
@@ -500,6 +501,8 @@ def main():
             ev.record(copy_stream)
         return b, ev
 
+    host_ms = [0.0]
+
     def run(nsteps, e2e):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -531,8 +534,10 @@ def main():
                 d0.synchronize()
                 loss_host.copy_(s0)
         else:
+            t_host = time.perf_counter()
             for i in range(nsteps):
                 model.training_step(batch, i)
+            host_ms[0] = (time.perf_counter() - t_host) * 1e3 / max(nsteps, 1)  # CPU time to ENQUEUE one step
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -580,7 +585,8 @@ def main():
                                                       "no explicit flush between steps"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "last_loss": loss_val,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks,
+        "last_loss": loss_val,
         **({"phase_ms": {k: round(v, 4) for k, v in phases.items()}} if phases else {}),
         "step_tensor_roofline": {"flops_per_image": fl_img, "achieved_tflops": value / world * fl_img / 1e12,
                                  "peak_tflops_sustained": peaks["tf_sust"],

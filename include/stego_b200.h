@@ -53,6 +53,16 @@ STEGO_API int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void
                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
                               void* stream);
 
+/* Fused residual GEMM + LayerNorm of a pre-norm transformer block (src/dino/vision_transformer.py:92-104,
+ * Block.forward:  x = x + proj(attn(...)) ; norm2(x)   and   x = x + fc2(...) ; next block's norm1(x)):
+ *     x[M][ldx] (fp32, in place) += A[M][lda] . W[N][ldw]^T + bias ;   y[M][ldy] (bf16) = LN(x) * gamma + beta
+ * with biased variance and `eps` inside the square root like nn.LayerNorm.  One CTA holds a whole output row in
+ * TMEM, so N must be 384 (ViT-S/8 embed dim) — other widths return STEGO_ERR_UNSUPPORTED and the caller uses
+ * stego_gemm_bf16 + stego_layernorm_bf16.  All pointers 16-byte aligned; K tail zero-filled by TMA. */
+STEGO_API int stego_gemm_residual_ln_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                                          float* x, int ldx, const float* bias, const float* gamma,
+                                          const float* beta, float eps, void* y, int ldy, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Frozen DINO ViT forward pieces (reference: src/dino/vision_transformer.py)
  * ---------------------------------------------------------------------------------------------- */
@@ -134,6 +144,13 @@ STEGO_API int stego_colsum(const void* in, int in_is_bf16, int ld, int C, long l
 STEGO_API int stego_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                               float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                               void* stream);
+
+/* The scalar arithmetic at the end of training_step (src/train_segmentation.py:196-201, 219-225) in one launch:
+ * out4[0] = sum_c call_weights_host[c] * corr_stats[c][0] + extra0[0] + extra1[0]   (total loss)
+ * out4[1] = the weighted correspondence term alone, out4[2] / out4[3] = mean loss / mean cd of calls 2.. (negatives).
+ * corr_stats is stego_corr_loss_fwd's `stats`; extra0/extra1 are device scalars or null; ncalls <= 16. */
+STEGO_API int stego_step_losses(const float* corr_stats, int ncalls, const float* call_weights_host,
+                                const float* extra0, const float* extra1, float* out4, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Probes

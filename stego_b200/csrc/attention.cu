@@ -89,6 +89,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       mbar_init(&o_full[b], 1);
     }
     fence_barrier_init();
+    // Q and the first K/V stages are requested BEFORE the CTA-wide sync / TMEM allocation: their L2/HBM latency
+    // overlaps the rest of the prologue (the barriers they signal were initialised by this very thread)
+    mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
+    tma_load_3d(smem + ATT_SMEM_Q, &tmQKV, q_full, head * ATT_D, q0, img);
+    tma_load_3d(smem + ATT_SMEM_Q + ATT_Q_BYTES / 2, &tmQKV, q_full, head * ATT_D, q0 + 64, img);
+    for (int j = 0; j < ATT_STAGES && j < nkv; ++j) {
+      uint8_t* sk = smem + ATT_SMEM_KV + j * 2 * ATT_KV_BYTES;
+      mbar_arrive_expect_tx(&kv_full[j], 2 * ATT_KV_BYTES);
+      tma_load_3d(sk, &tmQKV, &kv_full[j], p.E + head * ATT_D, j * ATT_BKV, img);
+      tma_load_3d(sk + ATT_KV_BYTES, &tmQKV, &kv_full[j], 2 * p.E + head * ATT_D, j * ATT_BKV, img);
+    }
   }
   if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -101,11 +112,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
-      tma_load_3d(smem + ATT_SMEM_Q, &tmQKV, q_full, head * ATT_D, q0, img);
-      tma_load_3d(smem + ATT_SMEM_Q + ATT_Q_BYTES / 2, &tmQKV, q_full, head * ATT_D, q0 + 64, img);
-      uint32_t stage = 0, phase = 0;
-      for (int j = 0; j < nkv; ++j) {
+      uint32_t stage = 0, phase = 1;  // tiles 0..STAGES-1 were requested in the prologue
+      for (int j = ATT_STAGES; j < nkv; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
         uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES;
         uint8_t* sv = sk + ATT_KV_BYTES;

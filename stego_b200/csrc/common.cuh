@@ -141,6 +141,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// L2-only prefetch of a tensor-map box (no shared memory, no barrier): pulls a tile's first touch out of HBM early
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // multicast variant: the box lands at the same CTA-relative smem offset in every CTA of `cta_mask` and performs
 // complete_tx on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

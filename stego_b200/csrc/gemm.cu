@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "host_util.h"
 
 namespace stego {
@@ -40,71 +41,8 @@ struct GemmParams {
   int vec_ok;         // host-verified 16-byte alignment of out/residual rows
   int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
   int tma_epi;        // 1: epilogue tiles leave through TMA stores; 2: TMA fp32 reduce-add (in-place residual)
+  int l2_prefetch;    // producer prefetches the A row block of its NEXT tile into L2 (first touch comes from HBM)
 };
-
-// Exact (erf) GELU, nn.GELU default.  erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one rcp + one ex2 on
-// the MUFU pipe and ~10 FMAs instead of the ~25-instruction erff — the fc1 epilogue is issue-bound otherwise.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));  // MUFU.RCP, no Newton fix-up
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erf_abs = fmaf(-poly, ex2_approx(-1.4426950408889634f * z * z), 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
-}
-
-// MUFU-free variant for bf16 outputs: erf(z) = z * P(z^2) (degree-9 minimax fit on |z| <= 3.2, clamped beyond;
-// |abs err| < 8.2e-6, i.e. < 2e-5 on GELU — two orders below bf16 rounding).  The fc1 epilogue applies GELU to
-// 77 M elements per layer; two MUFU ops per element made it MUFU-bound (16 ops/clk/SM).
-__device__ __forceinline__ float gelu_erf_poly(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 3.2f);
-  const float t = z * z;
-  float p = fmaf(t, -2.4003365851451727e-09f, 1.4192566410626377e-07f);
-  p = fmaf(p, t, -3.73997355423602e-06f);
-  p = fmaf(p, t, 5.846926586228758e-05f);
-  p = fmaf(p, t, -0.0006113043563036988f);
-  p = fmaf(p, t, 0.004584169635313263f);
-  p = fmaf(p, t, -0.025814482266624247f);
-  p = fmaf(p, t, 0.11186436329524356f);
-  p = fmaf(p, t, -0.37570728585235524f);
-  p = fmaf(p, t, 1.1283256165012454f);
-  const float e = fminf(p * z, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(e, x));
-}
-
-// bf16-output GELU, eight elements in lock-step (independent FMA chains), 13 instructions per element:
-//   erf(|x|/sqrt2) = xc * Q(xc^2), xc = min(|x|, 3.2*sqrt2), Q of degree 8 (minimax fit, |abs err| < 4.3e-5 in
-//   fp32 evaluation — two orders of magnitude below the bf16 rounding of the result), and
-//   gelu(x) = 0.5 x (1 + sign(x) erf(|x|/sqrt2)) = h + |h| * e with h = x/2.
-__device__ __forceinline__ void gelu_erf_poly8(float* x) {
-  float xc[8], u[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    xc[j] = fminf(fabsf(x[j]), 4.525483399593904f);
-    u[j] = xc[j] * xc[j];
-    q[j] = fmaf(u[j], 7.28493733954992e-11f, -7.739619932988917e-09f);
-  }
-#define STEGO_POLY_STEP(C) \
-  _Pragma("unroll") for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], u[j], C);
-  STEGO_POLY_STEP(3.6041332307651457e-07f)
-  STEGO_POLY_STEP(-9.764514095986007e-06f)
-  STEGO_POLY_STEP(0.0001730121070631224f)
-  STEGO_POLY_STEP(-0.0021448454598048446f)
-  STEGO_POLY_STEP(0.01943352726774955f)
-  STEGO_POLY_STEP(-0.13244709440462024f)
-  STEGO_POLY_STEP(0.7977185244870058f)
-#undef STEGO_POLY_STEP
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float e = q[j] * xc[j];
-    const float h = 0.5f * x[j];
-    x[j] = fmaf(fabsf(h), e, h);
-  }
-}
 
 template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -118,7 +56,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // accumulator (TMEM has 512 columns), two MMAs per k-step (N = 256 + 128), single epilogue staging tile.
   static_assert(BN == 128 || BN == 256 || BN == 384, "BN must be 128, 256 or 384");
   constexpr uint32_t kAccBufs = (BN == 384) ? 1u : 2u;
-  constexpr uint32_t kEpiBufs = (BN == 384) ? 1u : 2u;
+  constexpr uint32_t kEpiBufs = (BN == 384 || (BN == 256 && kStages >= 4)) ? 1u : 2u;  // staging tiles per epilogue warp
   constexpr uint32_t TMEM_COLS = (BN == 128) ? 256u : 512u;
   constexpr uint32_t N0 = (BN == 384) ? 256u : static_cast<uint32_t>(BN);  // first MMA of a k-step
   constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, N0, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
@@ -183,6 +121,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int tm = kCluster ? (t / tiles_n) * 2 + static_cast<int>(crank) : t / (p.splits * tiles_n);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        if (!A_MN && !kCluster && p.l2_prefetch) {
+          const int t2 = t + sched_step;
+          if (t2 < total_tiles) {
+            const int tm2 = t2 / (p.splits * tiles_n);
+            if (tm2 != tm)
+              for (int kb = kb0; kb < kb1; ++kb) tma_prefetch_l2_2d(&tmA, kb * GEMM_BK, tm2 * GEMM_BM);
+          }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -600,7 +546,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 8 * (BN == 384 ? 1 : 2) * 4096 + 1024 + 256;
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) +
+                          8 * ((BN == 384 || (BN == 256 && kStages >= 4)) ? 1 : 2) * 4096 + 1024 + 256;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, kCluster>;
   static bool configured = false;
   if (!configured) {
@@ -642,6 +589,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 using namespace stego;
 
+// gemm_2cta.cu: cta_group::2 kernel for the wide K-major linears
+int stego_launch_gemm_2cta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* out, int ldo,
+                           int out_bf16, const float* bias, int act, int reduce_add, cudaStream_t stream);
+
 // C-ABI: see include/stego_b200.h for the contract.
 extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
                                int N, int K, void* out, int ldo, int out_bf16, const float* bias, int act,
@@ -677,11 +628,18 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
   const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
   // 2-CTA clusters with TMA multicast of the shared B tile (K-major, no split-K, enough M tiles to pair up)
-  static int cluster_opt = -1;
+  static int cluster_opt = -1, prefetch_opt = 0, deep_opt = 0, two_cta_opt = 0;
   if (cluster_opt < 0) {
     const char* e = getenv("STEGO_GEMM_CLUSTER");
     cluster_opt = e ? atoi(e) : 0;
+    e = getenv("STEGO_GEMM_PREFETCH");
+    prefetch_opt = e ? atoi(e) : 0;
+    e = getenv("STEGO_GEMM_DEEP");
+    deep_opt = e ? atoi(e) : 0;
+    e = getenv("STEGO_GEMM_2CTA");
+    two_cta_opt = e ? atoi(e) : 0;
   }
+  p.l2_prefetch = prefetch_opt;
   const bool use_384 = !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
   const bool cluster = cluster_opt && !a_mn_major && !b_mn_major && splits == 1 && !atomic_out && M >= 512 && !use_384;
 
@@ -692,6 +650,10 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     if (residual == nullptr) p.tma_epi = 1;
     else if (!out_bf16 && residual == out && ldr == ldo) p.tma_epi = 2;
   }
+
+  // wide K-major linears (qkv, fc1): CTA pairs with UMMA M = 256, each CTA stages only half of the B tile
+  if (two_cta_opt && wide && p.tma_epi && M >= 256 && lda % 8 == 0)
+    return stego_launch_gemm_2cta(A, lda, B, ldb, M, N, K, out, ldo, out_bf16, bias, act, p.tma_epi == 2, stream);
 
   CUtensorMap tmA, tmB, tmO;
   int rc;
@@ -724,6 +686,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     if (wide) return launch_gemm<256, 3, false, false, true>(tmA, tmB, tmO, p, stream);
     return launch_gemm<128, 5, false, false, true>(tmA, tmB, tmO, p, stream);
   }
+  if (wide && deep_opt && p.tma_epi) return launch_gemm<256, 4, false, false>(tmA, tmB, tmO, p, stream);
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);

@@ -232,6 +232,42 @@ extern "C" int stego_colsum(const void* in, int in_is_bf16, int ld, int C, long 
   return STEGO_OK;
 }
 
+namespace stego {
+struct StepLossParams {
+  const float* stats;  // [ncalls][4] from stego_corr_loss_fwd
+  int ncalls;
+  float w[16];         // weight of each call's mean loss in the total
+  const float* extra0; // optional device scalars added to the total (linear / cluster probe losses)
+  const float* extra1;
+  float* out;          // [4]: total, weighted correspondence term, mean loss of calls 2.., mean cd of calls 2..
+};
+__global__ void step_losses_kernel(StepLossParams p) {
+  if (threadIdx.x != 0) return;
+  float corr = 0.f, neg = 0.f, negcd = 0.f;
+  for (int c = 0; c < p.ncalls; ++c) {
+    corr += p.w[c] * p.stats[c * 4];
+    if (c >= 2) { neg += p.stats[c * 4]; negcd += p.stats[c * 4 + 1]; }
+  }
+  const int nn = p.ncalls > 2 ? p.ncalls - 2 : 1;
+  float total = corr;
+  if (p.extra0) total += p.extra0[0];
+  if (p.extra1) total += p.extra1[0];
+  p.out[0] = total; p.out[1] = corr; p.out[2] = neg / nn; p.out[3] = negcd / nn;
+}
+}  // namespace stego
+
+extern "C" int stego_step_losses(const float* corr_stats, int ncalls, const float* call_weights_host,
+                                 const float* extra0, const float* extra1, float* out4, void* stream_) {
+  STEGO_CHECK_ARG(corr_stats && call_weights_host && out4, "stego_step_losses: null pointer");
+  STEGO_CHECK_ARG(ncalls >= 1 && ncalls <= 16, "stego_step_losses: ncalls=%d (1..16)", ncalls);
+  stego::StepLossParams p;
+  p.stats = corr_stats; p.ncalls = ncalls; p.extra0 = extra0; p.extra1 = extra1; p.out = out4;
+  for (int c = 0; c < 16; ++c) p.w[c] = c < ncalls ? call_weights_host[c] : 0.f;
+  stego::step_losses_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  STEGO_CHECK_LAUNCH("step_losses_kernel launch");
+  return stego::STEGO_OK;
+}
+
 extern "C" int stego_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                                float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                                void* stream_) {

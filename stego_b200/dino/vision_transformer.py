@@ -204,14 +204,26 @@ class VisionTransformer(nn.Module):
         ao = torch.empty(B * N, E, dtype=torch.bfloat16, device=dev)
         hid = torch.empty(B * N, w["blocks"][0]["fc1_w"].shape[0], dtype=torch.bfloat16, device=dev)
         Hd = hid.shape[1]
-        for bw in w["blocks"]:
-            ops.layernorm(x, bw["n1w"], bw["n1b"], y, eps=bw["eps1"])
+        # E == 384: the LayerNorm that follows each residual GEMM is computed in that GEMM's epilogue (one CTA holds
+        # a whole token row in TMEM), so the fp32 residual stream is not re-read by a separate LayerNorm kernel.
+        fused = ops.fused_ln_supported(E)
+        blocks = w["blocks"]
+        for i, bw in enumerate(blocks):
+            if i == 0 or not fused:
+                ops.layernorm(x, bw["n1w"], bw["n1b"], y, eps=bw["eps1"])
             ops.gemm(y, bw["qkv_w"], qkv, M=B * N, N=3 * E, K=E, bias=bw["qkv_b"])
             ops.attention(qkv, ao, B, N, E, heads)
-            ops.gemm(ao, bw["proj_w"], x, M=B * N, N=E, K=E, bias=bw["proj_b"], residual=x)
-            ops.layernorm(x, bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
+            if fused:
+                ops.gemm_residual_ln(ao, bw["proj_w"], x, bw["proj_b"], bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
+            else:
+                ops.gemm(ao, bw["proj_w"], x, M=B * N, N=E, K=E, bias=bw["proj_b"], residual=x)
+                ops.layernorm(x, bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
             ops.gemm(y, bw["fc1_w"], hid, M=B * N, N=Hd, K=E, bias=bw["fc1_b"], act=ops.ACT_GELU)
-            ops.gemm(hid, bw["fc2_w"], x, M=B * N, N=E, K=Hd, bias=bw["fc2_b"], residual=x)
+            if fused and i + 1 < len(blocks):
+                nx = blocks[i + 1]
+                ops.gemm_residual_ln(hid, bw["fc2_w"], x, bw["fc2_b"], nx["n1w"], nx["n1b"], y, eps=nx["eps1"])
+            else:
+                ops.gemm(hid, bw["fc2_w"], x, M=B * N, N=E, K=Hd, bias=bw["fc2_b"], residual=x)
         return x, (qkv if want_qkv else None)
 
     @torch.no_grad()
@@ -222,16 +234,23 @@ class VisionTransformer(nn.Module):
         use_graph=True replays the whole kernel sequence (~110 launches) as ONE CUDA graph captured per input
         shape (the backbone is frozen and RNG-free).  The result then lives in a static buffer that the next
         replay overwrites: only for callers that consume it before calling again (the fused training step)."""
-        if use_graph and img.is_cuda:
+        if use_graph and (img[0] if isinstance(img, (list, tuple)) else img).is_cuda:
             return self._graphed_patch_features(img)
+        if isinstance(img, (list, tuple)):
+            img = torch.cat(list(img), 0)
         return self._patch_features_eager(img)
 
-    def _graphed_patch_features(self, img: torch.Tensor) -> torch.Tensor:
+    def _graphed_patch_features(self, img) -> torch.Tensor:
+        """`img` may be a list of image batches: they are copied into consecutive slices of the graph's static
+        input (the fused step passes [img, img_pos] — no torch.cat of the two 19 MB batches)."""
         from .. import _lib
         self._prepared()
         graphs = self._cache.setdefault("graphs", {})
-        key = (tuple(img.shape), img.device.index)
+        parts = list(img) if isinstance(img, (list, tuple)) else [img]
+        shape = (sum(p.shape[0] for p in parts),) + tuple(parts[0].shape[1:])
+        key = (shape, parts[0].device.index)
         if key not in graphs:
+            img = torch.cat(parts, 0) if len(parts) > 1 else parts[0]
             self._patch_features_eager(img)  # warm-up: kernel attributes, pos-embed cache, allocator
             torch.cuda.synchronize()
             static_in = img.detach().float().contiguous().clone()
@@ -241,7 +260,10 @@ class VisionTransformer(nn.Module):
                 static_out = self._patch_features_eager(static_in)
             graphs[key] = (g, static_in, static_out, _lib.load().stego_launch_count() - n0)
         g, static_in, static_out, nlaunch = graphs[key]
-        static_in.copy_(img)
+        off = 0
+        for part in parts:
+            static_in[off:off + part.shape[0]].copy_(part)
+            off += part.shape[0]
         g.replay()
         _lib.replayed_launches += nlaunch
         return static_out

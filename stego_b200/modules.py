@@ -265,8 +265,9 @@ class DinoFeaturizer(nn.Module):
         """Frozen ViT -> bf16 tokens-major features [B, hw, E] (cls dropped).  use_graph: replay the kernel
         sequence as one CUDA graph (result is a static buffer valid until the next call)."""
         self.model.eval()
-        assert img.shape[2] % self.patch_size == 0
-        assert img.shape[3] % self.patch_size == 0
+        first = img[0] if isinstance(img, (list, tuple)) else img  # a list of batches is concatenated on the fly
+        assert first.shape[2] % self.patch_size == 0
+        assert first.shape[3] % self.patch_size == 0
         return self.model.patch_features(img, use_graph=use_graph)
 
     def draw_masks(self, batch: int, device):

@@ -195,6 +195,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         self.logged: Dict[str, torch.Tensor] = {}
         self._flat: Optional[FlatParams] = None
         self._spec = corr.LossSpec(cfg)
+        self._fused = None
         self.profile_marks = None  # optional list: bench.py --breakdown collects (name, cuda event) pairs here
 
     # ---- Lightning-shaped surface ----------------------------------------------------------------
@@ -227,6 +228,18 @@ class LitUnsupervisedSegmenter(nn.Module):
 
     # ---- the step ---------------------------------------------------------------------------------
     def training_step(self, batch, batch_idx):
+        """train_segmentation.py:112-245.  The shipped configuration (dino arch, correspondence loss, no salience /
+        rec / aug / crf terms) runs as the hand-scheduled kernel sequence of fused_step.FusedStep; anything else
+        (or cfg.fused_step = False) takes the autograd-stitched path below.  Both compute the same step."""
+        if getattr(self.cfg, "fused_step", True):
+            if self._fused is None:
+                from .fused_step import FusedStep
+                self._fused = FusedStep(self)
+            if self._fused.supported(batch):
+                return self._fused.run(batch)
+        return self._training_step_autograd(batch, batch_idx)
+
+    def _training_step_autograd(self, batch, batch_idx):
         cfg = self.cfg
         net_optim, linear_probe_optim, cluster_probe_optim = self.optimizers()
         net_optim.zero_grad()

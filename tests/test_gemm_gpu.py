@@ -127,3 +127,44 @@ def test_gemm_bad_args_raise(cuda_dev):
     out = torch.zeros(128, 128, device=cuda_dev)
     with pytest.raises(RuntimeError):
         ops.gemm(a, b, out, M=128, N=128, K=100)
+
+
+@pytest.mark.parametrize("M,K", [(128, 384), (1000, 384), (785 * 3, 1536), (50240, 384), (130, 200)])
+def test_gemm_residual_layernorm_fused(cuda_dev, M, K):
+    """x += a.w^T + b ; y = LN(x): the fused epilogue (one CTA holds the whole 384-wide row in TMEM) against fp32
+    torch on bf16-rounded operands; rows with a large mean / an outlier channel exercise the two-pass variance."""
+    from stego_b200 import ops
+    torch.manual_seed(5)
+    N = 384
+    a = torch.randn(M, K, device=cuda_dev).bfloat16()
+    w = (torch.randn(N, K, device=cuda_dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=cuda_dev)
+    x = torch.randn(M, N, device=cuda_dev) * 2 + 3.0
+    x[:, 7] += 60.0
+    gamma = torch.rand(N, device=cuda_dev) + 0.5
+    beta = torch.randn(N, device=cuda_dev)
+    want_x = x + a.float() @ w.float().t() + bias
+    want_y = torch.nn.functional.layer_norm(want_x, (N,), gamma, beta, 1e-6)
+    y = torch.full((M, N), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    ops.gemm_residual_ln(a, w, x, bias, gamma, beta, y, eps=1e-6)
+    assert _rel(x, want_x) < 1e-5
+    assert torch.isfinite(y.float()).all()
+    assert _rel(y, want_y) < 4e-3
+    assert (y.float() - want_y).abs().max().item() < 0.05 * want_y.abs().max().item() + 0.05
+    # no bias
+    x2 = want_x.clone()
+    ops.gemm_residual_ln(a, w, x2, None, gamma, beta, y, eps=1e-6)
+    want_x2 = want_x + a.float() @ w.float().t()
+    assert _rel(x2, want_x2) < 1e-5
+    assert _rel(y, torch.nn.functional.layer_norm(want_x2, (N,), gamma, beta, 1e-6)) < 4e-3
+
+
+def test_gemm_residual_layernorm_rejects_other_widths(cuda_dev):
+    from stego_b200 import ops
+    a = torch.zeros(128, 64, device=cuda_dev, dtype=torch.bfloat16)
+    w = torch.zeros(768, 64, device=cuda_dev, dtype=torch.bfloat16)
+    x = torch.zeros(128, 768, device=cuda_dev)
+    y = torch.zeros(128, 768, device=cuda_dev, dtype=torch.bfloat16)
+    g = torch.ones(768, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="N=768"):
+        ops.gemm_residual_ln(a, w, x, None, g, g, y)

@@ -109,13 +109,14 @@ def test_cluster_lookup_matches_oracle(cuda_dev):
         assert _rel(cl.clusters.grad, c_ref.grad) < 1e-4
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["handscheduled", "autograd"])
 @pytest.mark.parametrize("arch,res,B", [("vit_small", 224, 2), ("vit_small", 64, 4)])
-def test_training_step_matches_oracle(cuda_dev, arch, res, B):
+def test_training_step_matches_oracle(cuda_dev, arch, res, B, fused):
     import stego_oracle as O
     from stego_b200.config import make_cfg
     from stego_b200.modules import super_perm
     from stego_b200.segmenter import LitUnsupervisedSegmenter
-    cfg = make_cfg(model_type=arch, random_backbone_init=True)
+    cfg = make_cfg(model_type=arch, random_backbone_init=True, fused_step=fused)
     ocfg = O.LossCfg()
     torch.manual_seed(0)
     model = LitUnsupervisedSegmenter(27, cfg).to(cuda_dev)
@@ -140,6 +141,7 @@ def test_training_step_matches_oracle(cuda_dev, arch, res, B):
     perms = [super_perm(B, cuda_dev) for _ in range(5)]
     torch.manual_seed(777)
     loss = model.training_step(batch, 0)
+    assert (model._fused is not None and model._fused.step_idx == 1) == fused
     grads = {k: dict(model.named_parameters())[k].grad.detach().cpu().clone() for k in names}
     params1 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if k in names}
 
