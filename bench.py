@@ -380,7 +380,6 @@ def run_c4(args, rank, world, local):
         sampler.start()
     l0 = _lib.launch_count()
     ms_dev = run(args.steps, False)
-    host_enqueue_ms = host_ms[0]
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)
@@ -551,6 +550,7 @@ def main():
         sampler.start()
     l0 = _lib.launch_count()
     ms_dev = run(args.steps, False)
+    host_enqueue_ms = host_ms[0]
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)

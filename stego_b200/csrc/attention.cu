@@ -125,56 +125,65 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, ATT_BKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major: d contiguous)
-      const uint32_t sq = smem_u32(smem + ATT_SMEM_Q);
-      mbar_wait(q_full, 0);
+    // The whole warp walks the schedule (warp-uniform control flow keeps the descriptors in uniform registers; from
+    // inside an `if (lane == 0)` region every tcgen05.mma was preceded by ~17 instructions of per-thread descriptor
+    // rebuilding behind an ELECT/R2UR loop) and one elected lane issues.
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, ATT_BKV, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);       // P (K-major) x V (MN-major: d contiguous)
+    constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+    const uint32_t tm_s = __shfl_sync(0xffffffffu, TM_S, 0);
+    const uint32_t tm_o = __shfl_sync(0xffffffffu, TM_O, 0);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(smem + ATT_SMEM_Q), 16);
+    const uint32_t k_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV), 16);
+    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV + ATT_KV_BYTES), 8192);
+    const uint32_t p_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_P), 16);
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    auto issue_pv = [&](int i) {
+      const uint32_t b = static_cast<uint32_t>(i & 1);
+      const uint32_t it = static_cast<uint32_t>(i >> 1);
+      const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
+      mbar_wait(&p_full[b], it & 1u);  // P written (and O rescaled, if needed) by warpgroup b
       tc_fence_after();
-      auto issue_pv = [&](int i) {
-        const int b = i & 1;
-        const uint32_t it = static_cast<uint32_t>(i >> 1);
-        const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
-        mbar_wait(&p_full[b], it & 1u);  // P written (and O rescaled, if needed) by warpgroup b
-        tc_fence_after();
-        const uint32_t sp = smem_u32(smem + ATT_SMEM_P + b * ATT_P_BYTES);
-        const uint32_t sv = smem_u32(smem + ATT_SMEM_KV + stage_i * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
+      const uint32_t p_lo = p_lo0 + b * (ATT_P_BYTES >> 4);
+      const uint32_t v_lo = v_lo0 + stage_i * ((2 * ATT_KV_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sp + kk * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 8192, 1024);
-          umma_bf16(TM_O + b * 64, da, db, IDESC_O, (it > 0 || kk > 0) ? 1u : 0u);  // accumulate over this WG's tiles
-        }
+        for (uint32_t kk = 0; kk < ATT_BKV / 16; ++kk)  // accumulate over this warpgroup's tiles
+          umma_bf16(tm_o + b * 64, smem_desc_join(p_lo + kk * 2, DESC_HI), smem_desc_join(v_lo + kk * (2048u >> 4), DESC_HI),
+                    IDESC_O, (it > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&o_full[b]);
         umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
-      };
-      // S runs two tiles ahead of P V: the S buffer of tile j+2 is free as soon as the softmax warpgroup holds the
-      // scores of tile j in registers (early s_empty), so S_{j+2} is issued BEFORE the blocking wait for P_j and is
-      // ready when that warpgroup comes back.  (Blocking try_wait on purpose: a polling loop on this lane steals
-      // issue slots from the softmax warps of its SM sub-partition.)
-      auto issue_s = [&](int j) {
-        const int b = j & 1;
-        const uint32_t it = static_cast<uint32_t>(j >> 1);
-        const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
-        const uint32_t phase = static_cast<uint32_t>((j / ATT_STAGES) & 1);
-        mbar_wait(&kv_full[stage], phase);
-        mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sq + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sk + k * 32, 16, 1024);
-          umma_bf16(TM_S + b * ATT_BKV, da, db, IDESC_S, k > 0 ? 1u : 0u);
-        }
-        umma_commit(&s_full[b]);
-      };
-      const int ahead = p.s_ahead;
-      for (int j = 0; j < ahead && j < nkv; ++j) issue_s(j);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + ahead < nkv) issue_s(j + ahead);
-        issue_pv(j);
       }
+      __syncwarp();
+    };
+    // S runs two tiles ahead of P V: the S buffer of tile j+2 is free as soon as the softmax warpgroup holds the
+    // scores of tile j in registers (early s_empty), so S_{j+2} is issued BEFORE the blocking wait for P_j and is
+    // ready when that warpgroup comes back.  (Blocking try_wait on purpose: a polling loop on this warp steals
+    // issue slots from the softmax warps of its SM sub-partition.)
+    auto issue_s = [&](int j) {
+      const uint32_t b = static_cast<uint32_t>(j & 1);
+      const uint32_t it = static_cast<uint32_t>(j >> 1);
+      const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
+      const uint32_t phase = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+      mbar_wait(&kv_full[stage], phase);
+      mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t k_lo = k_lo0 + stage * ((2 * ATT_KV_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(tm_s + b * ATT_BKV, smem_desc_join(q_lo + k * 2, DESC_HI), smem_desc_join(k_lo + k * 2, DESC_HI), IDESC_S,
+                    k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    const int ahead = p.s_ahead;
+    for (int j = 0; j < ahead && j < nkv; ++j) issue_s(j);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + ahead < nkv) issue_s(j + ahead);
+      issue_pv(j);
     }
   } else {
     // ===================== softmax warpgroups =====================

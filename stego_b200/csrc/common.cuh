@@ -309,6 +309,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor split into its two 32-bit words: the high word is a compile-time constant and the low word is
+// (address >> 4) | LBO field, so stepping through a tile (next UMMA_K slice, next pipeline stage) is ONE integer add
+// on the low word instead of re-deriving all fields (the MMA-issuing thread is a serial bottleneck otherwise).
+// Valid while the address stays below 256 KB (14-bit field), which holds for shared memory.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulator.
 //   c_format [4,6)=1 (F32); a_format [7,10)=1 (BF16); b_format [10,13)=1 (BF16)
 //   a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major); n>>3 at [17,23); m>>4 at [24,29)

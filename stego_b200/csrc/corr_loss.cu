@@ -354,67 +354,89 @@ corr_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp walks the schedule (uniform control flow -> descriptors in uniform registers), one
+    // elected lane issues.  All descriptors are base-low-word + constant steps (see smem_desc_lo).
+    {
       constexpr uint32_t IDESC_KK = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+      constexpr uint32_t TILE16 = CL_TILE >> 4;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t tm_fd = tmem_u, tm_cd = tmem_u + 128, tm_da = tmem_u + 256, tm_db = tmem_u + 384;
+      const uint32_t ring_lo = smem_desc_lo(smem_u32(smem), 16);
       uint32_t stage = 0, phase = 0;
       // fd = An_f . Bn_f^T  (3 split passes over E)
       for (int pass = 0; pass < 3; ++pass) {
         for (int kb = 0; kb < nkb_f; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * 2 * CL_TILE);
+          const uint32_t a_lo = ring_lo + stage * 2 * TILE16;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(TM_FD, make_smem_desc_sw128(sa + k * 32, 16, 1024),
-                      make_smem_desc_sw128(sa + CL_TILE + k * 32, 16, 1024), IDESC_KK, (pass | kb | k) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            for (uint32_t k = 0; k < 4; ++k)
+              umma_bf16(tm_fd, smem_desc_join(a_lo + 2 * k, DESC_HI), smem_desc_join(a_lo + TILE16 + 2 * k, DESC_HI), IDESC_KK,
+                        (pass | kb | static_cast<int>(k)) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kRing) { stage = 0; phase ^= 1u; }
         }
       }
       // cd = An_c . Bn_c^T from the resident code tiles
       mbar_wait(code_full, 0);
       tc_fence_after();
-      const uint32_t sc = smem_u32(smem + OFF_CODE);
-      for (int pass = 0; pass < 3; ++pass) {
-        int pa, pb;
-        split_pass(pass, pa, pb);
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t sa = sc + (pa * 2 + kb) * CL_TILE;
-          const uint32_t sb = sc + (4 + pb * 2 + kb) * CL_TILE;
+      const uint32_t code_lo = smem_desc_lo(smem_u32(smem + OFF_CODE), 16);
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(TM_CD, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024),
-                      IDESC_KK, (pass | kb | k) ? 1u : 0u);
+        for (int pass = 0; pass < 3; ++pass) {
+          int pa, pb;
+          split_pass(pass, pa, pb);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t a_lo = code_lo + (pa * 2 + kb) * TILE16;
+            const uint32_t b_lo = code_lo + (4 + pb * 2 + kb) * TILE16;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+              umma_bf16(tm_cd, smem_desc_join(a_lo + 2 * k, DESC_HI), smem_desc_join(b_lo + 2 * k, DESC_HI), IDESC_KK,
+                        (pass | kb | static_cast<int>(k)) ? 1u : 0u);
+          }
         }
+        umma_commit(acc_full);
       }
-      umma_commit(acc_full);
+      __syncwarp();
       if (kBackward) {
         // G (bf16 hi/lo, [i][j] swizzled K-major image) is written by the epilogue warps into the ring area.
         mbar_wait(g_full, 0);
         tc_fence_after();
         constexpr uint32_t IDESC_K_MN = make_idesc_bf16(128, 128, 0, 1);   // A K-major, B MN-major
         constexpr uint32_t IDESC_MN_MN = make_idesc_bf16(128, 128, 1, 1);  // A MN-major, B MN-major
-        const uint32_t sg = smem_u32(smem);  // G planes: hi at +0, lo at +32 KB; j-blocks 16 KB apart
-        for (int pass = 0; pass < 3; ++pass) {
-          int pg, pc;
-          split_pass(pass, pg, pc);
-          const uint32_t g = sg + pg * 2 * CL_TILE;
-          const uint32_t bc = sc + (4 + pc * 2) * CL_TILE;  // Bc plane: c-blocks 16 KB apart, rows = j
-          const uint32_t ac = sc + (pc * 2) * CL_TILE;      // Ac plane: rows = i
+        // MN-major operands: LBO = CL_TILE (64-wide blocks 16 KB apart); G planes: hi at +0, lo at +32 KB
+        const uint32_t g_k_lo = ring_lo;                                          // G as K-major A operand
+        const uint32_t g_mn_lo = smem_desc_lo(smem_u32(smem), CL_TILE);           // G^T as MN-major A operand
+        const uint32_t code_mn_lo = smem_desc_lo(smem_u32(smem + OFF_CODE), CL_TILE);
+        if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // dA[i][c] += sum_j G[i][j] Bc[j][c]: A = G K-major (k = j), B = Bc MN-major (n = c contiguous)
-            umma_bf16(TM_DA, make_smem_desc_sw128(g + (kk >> 2) * CL_TILE + (kk & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(bc + kk * 2048, CL_TILE, 1024), IDESC_K_MN, (pass | kk) ? 1u : 0u);
-          }
+          for (int pass = 0; pass < 3; ++pass) {
+            int pg, pc;
+            split_pass(pass, pg, pc);
+            const uint32_t g_off = pg * 2 * TILE16;
+            const uint32_t bc_lo = code_mn_lo + (4 + pc * 2) * TILE16;  // Bc plane: c-blocks 16 KB apart, rows = j
+            const uint32_t ac_lo = code_mn_lo + (pc * 2) * TILE16;      // Ac plane: rows = i
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // dB[j][c] += sum_i G[i][j] Ac[i][c]: A = G^T as MN-major (m = j contiguous, k = i rows)
-            umma_bf16(TM_DB, make_smem_desc_sw128(g + kk * 2048, CL_TILE, 1024),
-                      make_smem_desc_sw128(ac + kk * 2048, CL_TILE, 1024), IDESC_MN_MN, (pass | kk) ? 1u : 0u);
+            for (uint32_t kk = 0; kk < 8; ++kk) {
+              // dA[i][c] += sum_j G[i][j] Bc[j][c]: A = G K-major (k = j), B = Bc MN-major (n = c contiguous)
+              umma_bf16(tm_da, smem_desc_join(g_k_lo + g_off + (kk >> 2) * TILE16 + (kk & 3) * 2, DESC_HI),
+                        smem_desc_join(bc_lo + kk * (2048u >> 4), DESC_HI), IDESC_K_MN, (pass | static_cast<int>(kk)) ? 1u : 0u);
+            }
+#pragma unroll
+            for (uint32_t kk = 0; kk < 8; ++kk) {
+              // dB[j][c] += sum_i G[i][j] Ac[i][c]: A = G^T as MN-major (m = j contiguous, k = i rows)
+              umma_bf16(tm_db, smem_desc_join(g_mn_lo + g_off + kk * (2048u >> 4), DESC_HI),
+                        smem_desc_join(ac_lo + kk * (2048u >> 4), DESC_HI), IDESC_MN_MN, (pass | static_cast<int>(kk)) ? 1u : 0u);
+            }
           }
+          umma_commit(d_full);
         }
-        umma_commit(d_full);
+        __syncwarp();
       }
     }
   } else {

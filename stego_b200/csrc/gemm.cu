@@ -42,6 +42,8 @@ struct GemmParams {
   int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
   int tma_epi;        // 1: epilogue tiles leave through TMA stores; 2: TMA fp32 reduce-add (in-place residual)
   int l2_prefetch;    // producer prefetches the A row block of its NEXT tile into L2 (first touch comes from HBM)
+  int diag;           // STEGO_GEMM_DIAG bit flags for phase timing ONLY (results are garbage): 1 skip the epilogue work,
+                      // 2 skip the MMAs, 4 skip the TMA loads
 };
 
 template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster>
@@ -113,7 +115,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !(p.diag & 4)) {
       uint32_t stage = 0, phase = 0;
       for (int t = sched_start; t < total_tiles; t += sched_step) {
         const int split = kCluster ? 0 : t % p.splits;
@@ -160,41 +162,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t acc = 0, acc_phase = 0;
-      for (int t = sched_start; t < total_tiles; t += sched_step) {
-        const int split = kCluster ? 0 : t % p.splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+    // The WHOLE warp walks the pipeline (warp-uniform control flow keeps addresses / descriptors in uniform registers)
+    // and one elected lane issues the tcgen05 instructions.  Issuing from inside an `if (lane == 0)` region made the
+    // compiler rebuild every descriptor from per-thread registers behind an ELECT/R2UR loop: ~70 dependent
+    // instructions per k-step, which — not the tensor pipe, TMA or L2 — set the 0.65 us k-step time of every variant.
+    uint32_t stage = 0, phase = 0;
+    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+    constexpr uint32_t A_KSTEP = A_MN ? (2048u >> 4) : (32u >> 4);  // low-word step per UMMA_K = 16
+    constexpr uint32_t B_KSTEP = B_MN ? (2048u >> 4) : (32u >> 4);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? 8192u : 16u);
+    const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192u : 16u);
+    for (int t = sched_start; t < total_tiles; t += sched_step) {
+      const int split = kCluster ? 0 : t % p.splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + acc * (TMEM_COLS / kAccBufs);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!(p.diag & 4)) mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (TMEM_COLS / kAccBufs);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+        const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
+        const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // K-major: advance 16 elements = 32 B inside the 128-B swizzle row.
-            // MN-major: advance 16 k-rows = 2048 B; 64-wide M/N blocks are 8192 B apart (LBO).
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (uint32_t k = 0; k < ((p.diag & 2) ? 0u : GEMM_BK / 16); ++k) {
+            const uint64_t da = smem_desc_join(a_lo + k * A_KSTEP, DESC_HI);
+            umma_bf16(tmem_d, da, smem_desc_join(b_lo + k * B_KSTEP, DESC_HI), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             if (BN == 384)  // columns 256..383 of the accumulator <- B rows 256..383
-              umma_bf16(tmem_d + 256, da, make_smem_desc_sw128(sb + 256 * 128 + k * 32, 16, 1024), IDESC_TAIL,
+              umma_bf16(tmem_d + 256, da, smem_desc_join(b_lo + ((256u * 128u) >> 4) + k * B_KSTEP, DESC_HI), IDESC_TAIL,
                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (kCluster) umma_commit_multicast(&empty_bar[stage], 0x3);  // release the stage in BOTH CTAs
           else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
@@ -218,6 +227,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.diag & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       const int row = tm * GEMM_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       int out_row = row, res_row = row;
@@ -640,6 +656,10 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     two_cta_opt = e ? atoi(e) : 0;
   }
   p.l2_prefetch = prefetch_opt;
+  {
+    const char* e = getenv("STEGO_GEMM_DIAG");  // read every call: bench.py toggles it between diagnostic timings
+    p.diag = e ? atoi(e) : 0;
+  }
   const bool use_384 = !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
   const bool cluster = cluster_opt && !a_mn_major && !b_mn_major && splits == 1 && !atomic_out && M >= 512 && !use_384;
 

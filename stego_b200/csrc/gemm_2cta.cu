@@ -147,25 +147,34 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // whole warp, uniform control flow (descriptors stay in uniform registers); one elected lane issues
+    if (leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + A_BYTES, 16);
       for (int t = sched_start; t < total_tiles; t += sched_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // both CTAs have drained this accumulator buffer
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_u + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // A rows + B halves of BOTH CTAs have landed
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k)
-            umma_bf16_2sm(tmem_d, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024),
-                          IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage], 0x3);  // the stage is reusable in both CTAs once these MMAs retire
+            for (uint32_t k = 0; k < G2_BK / 16; ++k)
+              umma_bf16_2sm(tmem_d, smem_desc_join(a_lo + 2 * k, DESC_HI), smem_desc_join(b_lo + 2 * k, DESC_HI), IDESC,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 0x3);  // the stage is reusable in both CTAs once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2sm(&tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
+        if (elect_one()) umma_commit_2sm(&tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -104,27 +104,36 @@ gemm_residual_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp, uniform control flow (descriptors stay in uniform registers); one elected lane issues
+    {
       uint32_t stage = 0, phase = 0, tphase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + GL_A_BYTES, 16);
       for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
         mbar_wait(tempty_bar, tphase ^ 1u);
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * GL_STAGE_BYTES);
-          const uint32_t sb = sa + GL_A_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (GL_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (GL_STAGE_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GL_BK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            umma_bf16(tmem_base, da, make_smem_desc_sw128(sb + k * 32, 16, 1024), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base + 256, da, make_smem_desc_sw128(sb + 256 * 128 + k * 32, 16, 1024), IDESC_TAIL,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (uint32_t k = 0; k < GL_BK / 16; ++k) {
+              const uint64_t da = smem_desc_join(a_lo + 2 * k, DESC_HI);
+              umma_bf16(tmem_u, da, smem_desc_join(b_lo + 2 * k, DESC_HI), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_u + 256, da, smem_desc_join(b_lo + ((256u * 128u) >> 4) + 2 * k, DESC_HI), IDESC_TAIL,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == GL_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        if (elect_one()) umma_commit(tfull_bar);
+        __syncwarp();
         tphase ^= 1u;
       }
     }

@@ -66,6 +66,7 @@ class FusedStep:
         f32, bf = torch.float32, torch.bfloat16
         nonlinear = net.proj_type == "nonlinear"
         ws.dims = (B, E, D, P, fh, fw, hw, M, nonlinear)
+        ws.num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
         # RNG outputs
         ws.M1 = torch.empty(2 * B, E, 1, 1, dtype=f32, device=dev)
         ws.M2 = torch.empty(2 * B, E, 1, 1, dtype=f32, device=dev) if nonlinear else None
@@ -223,8 +224,10 @@ class FusedStep:
         c1.bias.grad.copy_(ws.db_pad[:D])
 
         def splits_for(out_rows, out_cols):
+            # split-K so that tiles x splits fills ONE wave of the persistent GEMM (one CTA per SM): 3 x 49 = 147 and
+            # 9 x 16 = 144 CTAs on 148 SMs (64 splits made 192 / 297 CTAs = 2 and 3 rounds of a 148-CTA grid)
             tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
-            return max(1, min(64, M // 512, -(-296 // tiles)))
+            return max(1, min(M // 512, ws.num_sms // tiles))
         ops.gemm(ws.dyb, ws.x1, c1.weight.grad.view(D, E), M=D, N=E, K=M, a_mn=True, b_mn=True,
                  splits=splits_for(D, E), atomic=True)
         if nonlinear:

@@ -172,9 +172,11 @@ class _HeadFn(torch.autograd.Function):
         dyb = torch.empty(M, 128, dtype=torch.bfloat16, device=dev)
         _lib.check(lib.stego_cast_pad_bf16(_lib.ptr(dcode), dcode.stride(0), D, _lib.ptr(dyb), 128, M, _lib.stream()),
                    "stego_cast_pad_bf16")
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
         def splits_for(out_rows, out_cols):
             tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
-            return max(1, min(64, M // 512, -(-296 // tiles)))  # ~2 CTAs per SM, bounded atomic fan-in
+            return max(1, min(M // 512, sms // tiles))  # tiles x splits = one wave of the persistent GEMM grid
         # bias gradient: column sums over the padded row (padding columns of d(code) are zero) -> vector loads
         db_pad = torch.zeros(P, dtype=torch.float32, device=dev)
         _lib.check(lib.stego_colsum(_lib.ptr(dcode), 0, dcode.stride(0), P if dcode.shape[1] >= P else D, M,
