@@ -84,24 +84,24 @@ struct EpiArgs {
   int N;
 };
 
-template <int BN, uint32_t kEpiBufs>
+template <int BN, uint32_t kEpiBufs, int kParts>
 __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const EpiArgs& p, uint32_t taddr, uint8_t* buf0,
-                                                  uint32_t& epi_groups, int half, int lane, int col_tile0, int row_base) {
+                                                  uint32_t& epi_groups, int part, int lane, int col_tile0, int row_base) {
+  // kParts warps share one TMEM lane quarter and take every kParts-th column group.  32 accumulator columns are in
+  // registers at a time (the kernel runs 18 warps: 112 registers per thread).
   if (p.out_bf16) {
 #pragma unroll 1
-    for (int c = half; c < BN / 64; c += 2) {
+    for (int c = part; c < BN / 64; c += kParts) {
       const int col0 = col_tile0 + c * 64;
       if (col0 >= p.N) break;
-      uint32_t v0[32], v1[32];
-      tmem_ld32(taddr + c * 64, v0);
-      tmem_ld32(taddr + c * 64 + 32, v1);
       uint8_t* buf = buf0 + (epi_groups & (kEpiBufs - 1u)) * 4096;
       if (lane == 0) tma_wait_group_read<kEpiBufs - 1>();  // the store that last read this staging tile is done
       __syncwarp();
-      tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
-        uint32_t* v = hh ? v1 : v0;
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 64 + hh * 32, v);
+        tmem_ld_wait();
         const int cb = col0 + hh * 32;
         float x[32];
 #pragma unroll
@@ -140,7 +140,7 @@ __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const 
     }
   } else {
 #pragma unroll 1
-    for (int c = half; c < BN / 32; c += 2) {
+    for (int c = part; c < BN / 32; c += kParts) {
       const int col0 = col_tile0 + c * 32;
       if (col0 >= p.N) break;
       uint32_t v[32];

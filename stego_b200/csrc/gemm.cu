@@ -23,7 +23,11 @@ namespace stego {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+// warp 0 TMA, warp 1 MMA, then 8 epilogue warps (two per TMEM lane quarter).  16 epilogue warps (four per quarter)
+// were measured: the epilogue alone got 10-15 % faster but the whole kernel 8-12 % slower (qkv 55 -> 60 us, fc1 81 -> 91):
+// the extra warps compete with the TMA-fed mainloop for shared-memory bandwidth (profiles/r1_gemm_phases.md).
+__host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN == 384 ? 8 : 8; }
+__host__ __device__ constexpr int gemm_threads(int BN) { return 64 + 32 * gemm_epi_warps(BN); }
 
 struct GemmParams {
   int M, N, K;        // logical GEMM sizes; K is the reduction length
@@ -47,7 +51,7 @@ struct GemmParams {
 };
 
 template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, GemmParams p) {
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
@@ -58,7 +62,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // accumulator (TMEM has 512 columns), two MMAs per k-step (N = 256 + 128), single epilogue staging tile.
   static_assert(BN == 128 || BN == 256 || BN == 384, "BN must be 128, 256 or 384");
   constexpr uint32_t kAccBufs = (BN == 384) ? 1u : 2u;
-  constexpr uint32_t kEpiBufs = (BN == 384 || (BN == 256 && kStages >= 4)) ? 1u : 2u;  // staging tiles per epilogue warp
+  constexpr int kEpiWarps = gemm_epi_warps(BN);
+  constexpr int kParts = kEpiWarps / 4;      // warps sharing one TMEM lane quarter
+  constexpr uint32_t kEpiBufs = (BN == 384) ? 1u : 2u;  // staging tiles per epilogue warp
   constexpr uint32_t TMEM_COLS = (BN == 128) ? 256u : 512u;
   constexpr uint32_t N0 = (BN == 384) ? 256u : static_cast<uint32_t>(BN);  // first MMA of a k-step
   constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, N0, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
@@ -72,7 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr uint32_t EPI_BYTES = 8 * kEpiBufs * 4096;  // 32-row x 128-byte staging tiles per epilogue warp
+  constexpr uint32_t EPI_BYTES = kEpiWarps * kEpiBufs * 4096;  // 32-row x 128-byte staging tiles per epilogue warp
   uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
@@ -102,7 +108,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -208,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate column groups
+    const int half = (warp - 2) >> 2;    // the kParts warps of a quarter take alternate column groups
     uint32_t acc = 0, acc_phase = 0;
     uint32_t epi_groups = 0;  // bulk-store groups this warp has committed (selects the staging tile)
     for (int t = sched_start; t < total_tiles; t += sched_step) {
@@ -218,7 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
         const int prow = tm * GEMM_BM + quarter * 32 + lane;
         if (prow < p.M) {
-          for (int c = half; c < BN / 32; c += 2) {
+          for (int c = half; c < BN / 32; c += kParts) {
             const int pc = tn * BN + c * 32;
             if (pc < p.N)
               asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.residual + static_cast<size_t>(prow) * p.ldr + pc));
@@ -245,102 +251,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.tma_epi) {
         // ---- TMA epilogue: TMEM -> regs (bias/act) -> swizzled smem staging tile -> ONE bulk tensor store (or fp32
         //      reduce-add for the in-place residual update x += ...) per 32 x 128-byte tile.  No global load/store
-        //      instructions, edges clipped by the tensor map, staging double-buffered per warp.
-        uint8_t* buf0 = epi_smem + (warp - 2) * (kEpiBufs * 4096);
-        const int row_base = tm * GEMM_BM + quarter * 32;
-        if (p.out_bf16) {
-#pragma unroll 1
-          for (int c = half; c < BN / 64; c += 2) {
-            const int col0 = tn * BN + c * 64;
-            if (col0 >= p.N) break;
-            uint32_t v0[32], v1[32];
-            tmem_ld32(taddr + c * 64, v0);
-            tmem_ld32(taddr + c * 64 + 32, v1);
-            uint8_t* buf = buf0 + (epi_groups & (kEpiBufs - 1u)) * 4096;
-            if (lane == 0) tma_wait_group_read<kEpiBufs - 1>();  // the store that last read this staging tile is done with it
-            __syncwarp();
-            tmem_ld_wait();
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t* v = hh ? v1 : v0;
-              const int cb = col0 + hh * 32;
-              float x[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-              if (p.bias != nullptr && cb < p.N) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
-                  x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
-                }
-              }
-              if (p.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) gelu_erf_poly8(x + j);
-              } else if (p.act == 2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 w;
-                w.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
-                w.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
-                w.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
-                w.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
-                *reinterpret_cast<uint4*>(buf + sw128_offset(lane, hh * 4 + j)) = w;
-              }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(buf, &tmO, col0, row_base);
-              tma_commit_group();
-            }
-            ++epi_groups;
-          }
-        } else {
-#pragma unroll 1
-          for (int c = half; c < BN / 32; c += 2) {
-            const int col0 = tn * BN + c * 32;
-            if (col0 >= p.N) break;
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            uint8_t* buf = buf0 + (epi_groups & (kEpiBufs - 1u)) * 4096;
-            if (lane == 0) tma_wait_group_read<kEpiBufs - 1>();
-            __syncwarp();
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
-              }
-            }
-            if (p.act == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-            } else if (p.act == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(buf + sw128_offset(lane, j)) =
-                  make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (p.tma_epi == 2) tma_reduce_add_2d(buf, &tmO, col0, row_base);
-              else tma_store_2d(buf, &tmO, col0, row_base);
-              tma_commit_group();
-            }
-            ++epi_groups;
-          }
-        }
+        //      instructions, edges clipped by the tensor map (epilogue.cuh).
+        EpiArgs ea;
+        ea.bias = p.bias; ea.act = p.act; ea.out_bf16 = p.out_bf16; ea.reduce_add = (p.tma_epi == 2); ea.N = p.N;
+        epilogue_tma_tile<BN, kEpiBufs, kParts>(&tmO, ea, taddr, epi_smem + (warp - 2) * (kEpiBufs * 4096), epi_groups, half,
+                                                lane, tn * BN, tm * GEMM_BM + quarter * 32);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -355,7 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int rsub = lane >> 3, chunk = lane & 7;
         if (p.out_bf16) {
 #pragma unroll 1
-          for (int c = half; c < BN / 64; c += 2) {
+          for (int c = half; c < BN / 64; c += kParts) {
             const int col0 = tn * BN + c * 64;
             if (col0 >= p.N) break;
             uint32_t v0[32], v1[32];
@@ -408,7 +323,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else {
 #pragma unroll 1
-          for (int c = half; c < BN / 32; c += 2) {
+          for (int c = half; c < BN / 32; c += kParts) {
             const int col0 = tn * BN + c * 32;
             if (col0 >= p.N) break;
             const int col = col0 + chunk * 4;
@@ -472,7 +387,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         continue;
       }
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += kParts) {
         const int col0 = tn * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
@@ -562,8 +477,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) +
-                          8 * ((BN == 384 || (BN == 256 && kStages >= 4)) ? 1 : 2) * 4096 + 1024 + 256;
+  constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + gemm_epi_warps(BN) * (BN == 384 ? 1 : 2) * 4096 + 1024 + 256;
+  static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, kCluster>;
   static bool configured = false;
   if (!configured) {
@@ -579,7 +494,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (pairs < clusters) clusters = pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(BN));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -596,7 +511,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int tiles = tiles_m * tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p);
+  kern<<<grid, gemm_threads(BN), smem, stream>>>(tmA, tmB, tmO, p);
   STEGO_CHECK_LAUNCH("gemm_bf16_kernel launch");
   return STEGO_OK;
 }
@@ -644,14 +559,12 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
   const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
   // 2-CTA clusters with TMA multicast of the shared B tile (K-major, no split-K, enough M tiles to pair up)
-  static int cluster_opt = -1, prefetch_opt = 0, deep_opt = 0, two_cta_opt = 0;
+  static int cluster_opt = -1, prefetch_opt = 0, two_cta_opt = 0;
   if (cluster_opt < 0) {
     const char* e = getenv("STEGO_GEMM_CLUSTER");
     cluster_opt = e ? atoi(e) : 0;
     e = getenv("STEGO_GEMM_PREFETCH");
     prefetch_opt = e ? atoi(e) : 0;
-    e = getenv("STEGO_GEMM_DEEP");
-    deep_opt = e ? atoi(e) : 0;
     e = getenv("STEGO_GEMM_2CTA");
     two_cta_opt = e ? atoi(e) : 0;
   }
@@ -706,7 +619,6 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     if (wide) return launch_gemm<256, 3, false, false, true>(tmA, tmB, tmO, p, stream);
     return launch_gemm<128, 5, false, false, true>(tmA, tmB, tmO, p, stream);
   }
-  if (wide && deep_opt && p.tma_epi) return launch_gemm<256, 4, false, false>(tmA, tmB, tmO, p, stream);
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);

@@ -190,7 +190,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_tma_tile<BN, kEpiBufs>(&tmO, p.epi, taddr, buf0, epi_groups, half, lane, tn * BN, row_base);
+      epilogue_tma_tile<BN, kEpiBufs, 2>(&tmO, p.epi, taddr, buf0, epi_groups, half, lane, tn * BN, row_base);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
