@@ -34,7 +34,9 @@ def timeit(fn, iters=8):
     return ts[len(ts) // 2]
 
 
-modes = [("full", 0), ("no softmax math (TMA + MMA + barrier protocol)", 1), ("barrier protocol only", 7),
+modes = [("full", 0), ("no KV tiles: launch + prologue + merge + output store", 8 | 4),
+         ("no KV tiles, no output store", 8 | 4 | 16), ("no softmax math (TMA + MMA + barrier protocol)", 1),
+         ("barrier protocol only", 7),
          ("softmax + barriers (no TMA, no MMA)", 6), ("softmax + MMA (no TMA)", 4), ("softmax + TMA (no MMA)", 2)]
 print("| mode | us |\n|---|---|")
 for name, d in modes:

@@ -7,16 +7,10 @@
 // P (bf16) goes through swizzled shared memory straight back into the tensor core for P V.
 //
 // One CTA per (128-query tile, head, image), head_dim = 64, 320 threads:
-//   warp 0      TMA producer: Q tile once, then a 4-stage ring of (K,V) tiles
-//   warp 1      allocates / frees TMEM, otherwise idle
+//   warp 0      TMA producer: Q tile once, then a 3-stage ring of (K,V) tiles
+//   warp 1      MMA issuer  : S_j = Q K_j^T (128x128x64), O_j = P_j V_j (128x64x128)
 //   warps 2..5  softmax warpgroup 0  (KV tiles 0,2,4,..)   } each thread owns one query row, keeps its own
 //   warps 6..9  softmax warpgroup 1  (KV tiles 1,3,5,..)   } reference max / running sum
-// Each warpgroup ISSUES ITS OWN tcgen05.mma (its first warp, one elected lane): S_{j+2} = Q K_{j+2}^T as soon as its
-// four warps hold S_j in registers (128-thread named barrier), P_j V_j as soon as its P tile is in shared memory
-// (second named barrier).  A separate MMA warp put two mbarrier hand-offs (softmax -> issuer -> softmax, ~0.4 us
-// each) on the critical path of every KV tile: with all math removed the kernel still took 68 of its 147 us
-// (profiles/r1_attn_phases_before.md).  Now every mbarrier the softmax warps wait on (S ready, P V retired, K/V
-// landed) was signalled about one tile earlier.
 // O accumulates IN TMEM across a warpgroup's KV tiles (tcgen05.mma accumulate), so the softmax warps never wait
 // for P V inside the loop.  The running max is updated lazily (FA4-style): the reference max only moves when the
 // new row max exceeds it by more than 2^8, and only then is O rescaled in TMEM (tcgen05.ld -> scale ->
@@ -46,7 +40,7 @@ constexpr uint32_t ATT_P_BYTES = 128 * 64 * 2;   // 16 KB [128 q][64 kv]
 constexpr uint32_t ATT_SMEM_Q = 0;
 constexpr uint32_t ATT_SMEM_KV = ATT_Q_BYTES;                                   // stages x (K,V)
 constexpr uint32_t ATT_SMEM_P = ATT_SMEM_KV + ATT_STAGES * 2 * ATT_KV_BYTES;    // one P tile per warpgroup
-constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_P + ATT_P_BYTES;  // m,l of WG1 (2 x 128 floats) reuse ITS P tile after its last P V
+constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_Q;  // m,l of WG1 (2 x 128 floats) reuse the Q tile once every S has been issued
 constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_P + 2 * ATT_P_BYTES;
 constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256;  // 112.25 KB: two CTAs per SM (<= 113 KB each)
 
@@ -55,11 +49,13 @@ struct AttnParams {
   int N;       // tokens per image
   int E;       // embed dim = heads * 64
   float scale_log2e;  // head_dim^-0.5 * log2(e)
-  int diag;           // STEGO_ATT_DIAG phase-timing flags (results garbage): 1 skip softmax math, 2 skip MMAs, 4 skip TMA
+  int s_ahead;        // how many KV tiles S = QK^T is issued ahead of P V (1 or 2)
+  int diag;           // STEGO_ATT_DIAG phase-timing flags (results garbage): 1 skip softmax math, 2 skip MMAs, 4 skip TMA,
+                      // 8 no KV tiles at all (prologue + merge + store only), 16 skip the output stores
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, AttnParams p) {
   // no static shared memory in this kernel: the dynamic window starts at offset 0 of the CTA's allocation and the
   // __align__(1024) below is honoured (128B-swizzled tiles need 1024-byte alignment); checked at run time.
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -69,7 +65,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   uint64_t* kv_full = bars + 1;                   // [STAGES]
   uint64_t* kv_empty = kv_full + ATT_STAGES;      // [STAGES]
   uint64_t* s_full = kv_empty + ATT_STAGES;       // [2]
-  uint64_t* o_full = s_full + 2;                  // [2]
+  uint64_t* s_empty = s_full + 2;                 // [2]
+  uint64_t* p_full = s_empty + 2;                 // [2]
+  uint64_t* o_full = p_full + 2;                  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -77,10 +75,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
   const int q0 = blockIdx.x * ATT_BQ;
   const int head = blockIdx.y;
   const int img = blockIdx.z;
-  const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
+  const int nkv = (p.diag & 8) ? 0 : (p.N + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmOut);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -88,6 +87,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 4);
+      mbar_init(&p_full[b], 4);
       mbar_init(&o_full[b], 1);
     }
     fence_barrier_init();
@@ -128,7 +129,67 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       }
     }
   } else if (warp == 1) {
-    // TMEM owner only (allocation above, deallocation at the end)
+    // ===================== MMA issuer =====================
+    // The whole warp walks the schedule (warp-uniform control flow keeps the descriptors in uniform registers; from
+    // inside an `if (lane == 0)` region every tcgen05.mma was preceded by ~17 instructions of per-thread descriptor
+    // rebuilding behind an ELECT/R2UR loop) and one elected lane issues.
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, ATT_BKV, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);       // P (K-major) x V (MN-major: d contiguous)
+    constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
+    const uint32_t tm_s = __shfl_sync(0xffffffffu, TM_S, 0);
+    const uint32_t tm_o = __shfl_sync(0xffffffffu, TM_O, 0);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(smem + ATT_SMEM_Q), 16);
+    const uint32_t k_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV), 16);
+    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV + ATT_KV_BYTES), 8192);
+    const uint32_t p_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_P), 16);
+    if (!(p.diag & 4)) mbar_wait(q_full, 0);
+    tc_fence_after();
+    auto issue_pv = [&](int i) {
+      const uint32_t b = static_cast<uint32_t>(i & 1);
+      const uint32_t it = static_cast<uint32_t>(i >> 1);
+      const uint32_t stage_i = static_cast<uint32_t>(i % ATT_STAGES);
+      mbar_wait(&p_full[b], it & 1u);  // P written (and O rescaled, if needed) by warpgroup b
+      tc_fence_after();
+      const uint32_t p_lo = p_lo0 + b * (ATT_P_BYTES >> 4);
+      const uint32_t v_lo = v_lo0 + stage_i * ((2 * ATT_KV_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t kk = 0; kk < ((p.diag & 2) ? 0u : ATT_BKV / 16); ++kk)  // accumulate over this warpgroup's tiles
+          umma_bf16(tm_o + b * 64, smem_desc_join(p_lo + kk * 2, DESC_HI), smem_desc_join(v_lo + kk * (2048u >> 4), DESC_HI),
+                    IDESC_O, (it > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&o_full[b]);
+        umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
+      }
+      __syncwarp();
+    };
+    // S runs two tiles ahead of P V: the S buffer of tile j+2 is free as soon as the softmax warpgroup holds the
+    // scores of tile j in registers (early s_empty), so S_{j+2} is issued BEFORE the blocking wait for P_j and is
+    // ready when that warpgroup comes back.  (Blocking try_wait on purpose: a polling loop on this warp steals
+    // issue slots from the softmax warps of its SM sub-partition.)
+    auto issue_s = [&](int j) {
+      const uint32_t b = static_cast<uint32_t>(j & 1);
+      const uint32_t it = static_cast<uint32_t>(j >> 1);
+      const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
+      const uint32_t phase = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+      if (!(p.diag & 4)) mbar_wait(&kv_full[stage], phase);
+      mbar_wait(&s_empty[b], (it & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t k_lo = k_lo0 + stage * ((2 * ATT_KV_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t k = 0; k < ((p.diag & 2) ? 0u : ATT_D / 16); ++k)
+          umma_bf16(tm_s + b * ATT_BKV, smem_desc_join(q_lo + k * 2, DESC_HI), smem_desc_join(k_lo + k * 2, DESC_HI), IDESC_S,
+                    k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    const int ahead = p.s_ahead;
+    for (int j = 0; j < ahead && j < nkv; ++j) issue_s(j);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + ahead < nkv) issue_s(j + ahead);
+      issue_pv(j);
+    }
   } else {
     // ===================== softmax warpgroups =====================
     const int wg = (warp - 2) >> 2;  // 0 or 1
@@ -141,66 +202,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const float c = p.scale_log2e;
     const uint32_t to = TM_O + wg * 64 + lane_off;
 
-    // ---- tcgen05 issue by this warpgroup's first warp (warp-uniform code, one elected lane; see gemm.cu) ----
-    const bool issuer = ((warp - 2) & 3) == 0;
-    constexpr uint32_t IDESC_S = make_idesc_bf16(128, ATT_BKV, 0, 0);  // Q (K-major) x K (K-major)
-    constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, 0, 1);       // P (K-major) x V (MN-major: d contiguous)
-    constexpr uint32_t DESC_HI = smem_desc_hi_sw128(1024);
-    const uint32_t tm_s = __shfl_sync(0xffffffffu, TM_S, 0) + wg * ATT_BKV;
-    const uint32_t tm_o = __shfl_sync(0xffffffffu, TM_O, 0) + wg * 64;
-    const uint32_t q_lo = smem_desc_lo(smem_u32(smem + ATT_SMEM_Q), 16);
-    const uint32_t k_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV), 16);
-    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem + ATT_SMEM_KV + ATT_KV_BYTES), 8192);
-    const uint32_t p_lo = smem_desc_lo(smem_u32(sp), 16);
-    auto issue_s = [&](int j) {  // S_j = Q K_j^T into this warpgroup's S buffer (free: all four warps hold S_{j-2})
-      const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
-      if (!(p.diag & 4)) mbar_wait(&kv_full[stage], static_cast<uint32_t>((j / ATT_STAGES) & 1));
-      tc_fence_after();
-      const uint32_t k_lo = k_lo0 + stage * ((2 * ATT_KV_BYTES) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (uint32_t k = 0; k < ((p.diag & 2) ? 0u : ATT_D / 16); ++k)
-          umma_bf16(tm_s, smem_desc_join(q_lo + k * 2, DESC_HI), smem_desc_join(k_lo + k * 2, DESC_HI), IDESC_S,
-                    k > 0 ? 1u : 0u);
-        umma_commit(&s_full[wg]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int j, bool accumulate) {  // O += P_j V_j; frees the K/V stage of tile j
-      const uint32_t stage = static_cast<uint32_t>(j % ATT_STAGES);
-      tc_fence_after();
-      const uint32_t v_lo = v_lo0 + stage * ((2 * ATT_KV_BYTES) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (uint32_t kk = 0; kk < ((p.diag & 2) ? 0u : ATT_BKV / 16); ++kk)
-          umma_bf16(tm_o, smem_desc_join(p_lo + kk * 2, DESC_HI), smem_desc_join(v_lo + kk * (2048u >> 4), DESC_HI), IDESC_O,
-                    (accumulate || kk > 0) ? 1u : 0u);
-        umma_commit(&o_full[wg]);
-        umma_commit(&kv_empty[stage]);
-      }
-      __syncwarp();
-    };
-    const int bar_s = 2 + wg, bar_p = 4 + wg;  // named barriers of this warpgroup (1 = the merge barrier below)
-    if (issuer && wg < nkv) {
-      if (!(p.diag & 4)) mbar_wait(q_full, 0);
-      issue_s(wg);
-    }
-
     uint32_t it = 0;
     for (int j = wg; j < nkv; j += 2, ++it) {
       const int valid = p.N - j * ATT_BKV;  // number of real keys in this tile (>= 1)
       mbar_wait(&s_full[wg], it & 1u);
       tc_fence_after();
       if (!warp_has_rows || (p.diag & 1)) {
-        // ragged last query tile (N = hw + 1): this warp's 32 rows are all padding — keep the protocol, skip the
-        // loads / exponentials / stores (their P rows and O rows are never read back)
-        tc_fence_before();
-        asm volatile("bar.sync %0, 128;\n" ::"r"(bar_s) : "memory");
-        if (issuer && j + 2 < nkv) issue_s(j + 2);
+        // ragged last query tile (N = hw + 1): this warp's 32 rows are all padding — keep the barrier protocol,
+        // skip the loads / exponentials / stores (their P rows and O rows are never read back)
+        if (lane == 0) mbar_arrive(&s_empty[wg]);
         if (it > 0) mbar_wait(&o_full[wg], (it - 1u) & 1u);
-        tc_fence_before();
-        asm volatile("bar.sync %0, 128;\n" ::"r"(bar_p) : "memory");
-        if (issuer) issue_pv(j, it > 0);
+        if (lane == 0) mbar_arrive(&p_full[wg]);
         continue;
       }
       const uint32_t ts = TM_S + wg * ATT_BKV + lane_off;
@@ -210,14 +222,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       tmem_ld32(ts + 32, v[1]);
       tmem_ld_wait();
       tc_fence_before();
-      asm volatile("bar.sync %0, 128;\n" ::"r"(bar_s) : "memory");  // all four warps hold S_j in registers
-      if (issuer && j + 2 < nkv) issue_s(j + 2);                     // ... so the S buffer can take the next tile now
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[wg]);  // S buffer is free for the MMA warp as soon as it is in registers
       float mx = -INFINITY;
       if (valid >= ATT_BKV) {
+        float mxb = -INFINITY;  // two independent FMNMX3 chains (one per 32-column half): half the dependent latency
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[h][t]));  // FMNMX3 chain (a hand-made tree was slower)
+        for (int t = 0; t < 32; ++t) {
+          mx = fmaxf(mx, __uint_as_float(v[0][t]));
+          mxb = fmaxf(mxb, __uint_as_float(v[1][t]));
+        }
+        mx = fmaxf(mx, mxb);
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -256,22 +271,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       // Full tiles (all but the last) take the select-free path: a per-element mask costs an ISETP + FSEL each.
       float rs = 0.f;
       if (valid >= ATT_BKV) {
+        // packed fp32x2 FMA / ADD: the scale-and-shift and the row sum take half the issue slots of the scalar form
+        const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+        uint64_t rs2a = 0ull, rs2b = 0ull;  // two independent (0.f, 0.f) accumulators
+        uint8_t* prow = sp + r * 128;
+        const uint32_t rx = (static_cast<uint32_t>(r) & 7u) << 4;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float e[8];
+            uint32_t wv[4];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) e[t] = ex2_approx(fmaf(__uint_as_float(v[h][8 * g + t]), c, -mc));
-            uint4 w;
-            w.x = pack_bf16x2(e[0], e[1]);
-            w.y = pack_bf16x2(e[2], e[3]);
-            w.z = pack_bf16x2(e[4], e[5]);
-            w.w = pack_bf16x2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(sp + sw128_offset(r, h * 4 + g)) = w;
-            rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            for (int t = 0; t < 4; ++t) {
+              const uint64_t s2 = pack_f32x2(__uint_as_float(v[h][8 * g + 2 * t]), __uint_as_float(v[h][8 * g + 2 * t + 1]));
+              float a0, a1;
+              unpack_f32x2(fma_f32x2(s2, c2, nmc2), a0, a1);
+              const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+              wv[t] = pack_bf16x2(e0, e1);
+              if (t & 1) rs2b = add_f32x2(rs2b, pack_f32x2(e0, e1));
+              else rs2a = add_f32x2(rs2a, pack_f32x2(e0, e1));
+            }
+            *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(h * 4 + g) << 4) ^ rx)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
         }
+        float s0, s1;
+        unpack_f32x2(add_f32x2(rs2a, rs2b), s0, s1);
+        rs = s0 + s1;
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -296,23 +321,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       l_run += rs;
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      asm volatile("bar.sync %0, 128;\n" ::"r"(bar_p) : "memory");  // the whole P_j tile is written (and O rescaled)
-      if (issuer) issue_pv(j, !first);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
     }
     // ---- combine the two warpgroups (split-KV merge) and write the output ----
     // Both O accumulators live in the SAME TMEM lanes (rows), 64 columns apart, so warpgroup 0 reads both
     // straight out of TMEM; only m and l of warpgroup 1 travel through shared memory.
     float* ml = reinterpret_cast<float*>(smem + ATT_SMEM_ML);  // [2][128]
     if (wg == 1) {
-      // ml aliases this warpgroup's own P tile: its last P V must have retired
+      // ml aliases the Q tile: every S = Q K^T must have retired first.  tcgen05.commit covers all earlier MMAs of
+      // the issuing thread, and every S is issued before this warpgroup's last P V, so its o_full is sufficient
+      // (with no tile of its own — a single KV tile — wait for S_0 instead).
       if (it > 0) mbar_wait(&o_full[1], (it - 1u) & 1u);
+      else if (!(p.diag & 8)) mbar_wait(&s_full[0], 0);
       ml[r] = m_run;
       ml[128 + r] = l_run;
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 softmax warps only
     if (wg == 0) {
       const uint32_t it1 = static_cast<uint32_t>(nkv / 2);  // tiles warpgroup 1 processed (it = tiles of WG0 >= 1)
-      mbar_wait(&o_full[0], (it - 1u) & 1u);
+      if (it > 0) mbar_wait(&o_full[0], (it - 1u) & 1u);
       if (it1 > 0) mbar_wait(&o_full[1], (it1 - 1u) & 1u);
       tc_fence_after();
       const float m1 = ml[r], l1 = ml[128 + r];
@@ -321,15 +349,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
       const float a1 = (it1 == 0 || m1 == -INFINITY) ? 0.f : ex2_approx((m1 - m) * c);
       const float inv = 1.0f / (l_run * a0 + l1 * a1);
       const float s0 = a0 * inv, s1 = a1 * inv;
-      const int q = q0 + r;
-      bf16* o = p.out + (static_cast<size_t>(img) * p.N + q) * p.E + head * ATT_D;
+      // The [128 q][64 d] bf16 output tile is staged in this warpgroup's (now idle) P tile and leaves as two TMA bulk
+      // stores: one thread per row writing 8 x 16 B straight to global cost 1024 LSU wavefronts per CTA (14 of the
+      // kernel's ~150 us with nothing else running, profiles/r1_attn_phases_before.md); rows >= N are clipped by the map.
+      uint8_t* stage_row = sp + r * 128;
+      const uint32_t rx = (static_cast<uint32_t>(r) & 7u) << 4;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         uint32_t v0[32], v1[32];
         tmem_ld32(TM_O + lane_off + h * 32, v0);
         tmem_ld32(TM_O + 64 + lane_off + h * 32, v1);  // never-written columns if it1 == 0: multiplied by s1 = 0
         tmem_ld_wait();
-        if (q < p.N) {
+        {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float y[8];
@@ -343,9 +374,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             w.y = pack_bf16x2(y[2], y[3]);
             w.z = pack_bf16x2(y[4], y[5]);
             w.w = pack_bf16x2(y[6], y[7]);
-            reinterpret_cast<uint4*>(o)[h * 4 + g] = w;
+            *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(h * 4 + g) << 4) ^ rx)) = w;
           }
         }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 128;\n" ::: "memory");  // warpgroup 0 only: the whole tile is staged
+      if (warp == 2 && lane == 0 && !(p.diag & 16)) {
+        tma_store_3d(sp, &tmOut, head * ATT_D, q0, img);
+        tma_store_3d(sp + 64 * 128, &tmOut, head * ATT_D, q0 + 64, img);
+        tma_commit_group();
+        tma_wait_group_read<0>();  // the staging tile must outlive the bulk stores
       }
     }
   }
@@ -375,6 +414,10 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
   uint32_t box[3] = {64, 64, 1};  // one 64-row box serves K, V (one load) and Q (two loads)
   int rc = make_tmap_bf16(&tm, qkv, 3, dims, str, box);
   if (rc != STEGO_OK) return rc;
+  CUtensorMap tmo;  // output [B][N][E]: per-image row clipping for the ragged last query tile
+  uint64_t odims[3] = {(uint64_t)E, (uint64_t)N, (uint64_t)B};
+  uint64_t ostr[2] = {(uint64_t)E * 2, (uint64_t)N * E * 2};
+  if ((rc = make_tmap_bf16(&tmo, out, 3, odims, ostr, box)) != STEGO_OK) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -388,11 +431,17 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
   p.E = E;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   {
+    static int ahead = 0;
+    if (ahead == 0) {
+      const char* e = getenv("STEGO_ATT_S_AHEAD");
+      ahead = (e && e[0] == '1') ? 1 : 2;
+    }
+    p.s_ahead = ahead;
     const char* dg = getenv("STEGO_ATT_DIAG");  // read every call (profiles/attn_phases.py toggles it)
     p.diag = dg ? atoi(dg) : 0;
   }
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, p);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, tmo, p);
   STEGO_CHECK_LAUNCH("attention_fwd_kernel");
   return STEGO_OK;
 }
