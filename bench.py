@@ -171,10 +171,10 @@ def time_cpu(model_type, res, batch, steps, warmup, budget_s=150.0):
         avail = len(os.sched_getaffinity(0))
     except Exception:
         avail = os.cpu_count() or 1
-    cands = sorted({c for c in (avail, 32, 16, 8) if c <= avail}, reverse=True) or [avail]
-    torch.set_num_threads(cands[-1])
+    cands = sorted({c for c in (avail, 32, 16, 8) if c <= avail}) or [avail]  # ascending: cheap probes first
+    torch.set_num_threads(cands[0])
     step()  # warm-up (allocator, MKL init)
-    best_t, best_c = None, cands[-1]
+    best_t, best_c = None, cands[0]
     t_spent = 0.0
     for c in cands:
         if best_t is not None and t_spent > budget_s / 3:
@@ -186,6 +186,8 @@ def time_cpu(model_type, res, batch, steps, warmup, budget_s=150.0):
         t_spent += dt
         if best_t is None or dt < best_t:
             best_t, best_c = dt, c
+        elif dt > 1.5 * best_t:
+            break  # more threads are already making it slower (oversubscribed pool): do not probe the larger counts
     torch.set_num_threads(best_c)
     steps = max(1, min(steps, int(max(budget_s - t_spent, 1.0) / max(best_t, 1e-3))))
     t0 = time.perf_counter()
