@@ -22,7 +22,9 @@ def launches(path):
         t = t / 1e3 if unit == "ns" else (t * 1e3 if unit == "ms" else t)
         order.append((re.sub(r"\(.*", "", row["Kernel Name"])[:70], t))
     n = len(order)
-    q = order[-(n // 4):]  # bench.py --steps 1 --warmup 1 runs 4 steps (2 device-resident, 2 e2e): last quarter = one step
+    # one step = from a patchify launch (first kernel of the ViT) to the next one; take the last complete step
+    starts = [i for i, (s, _) in enumerate(order) if "patchify" in s]
+    q = order[starts[-2]:starts[-1]] if len(starts) >= 2 else order[-(n // 4):]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for s, t in q:
         agg[s][0] += 1

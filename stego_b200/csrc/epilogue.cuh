@@ -38,20 +38,27 @@ __device__ __forceinline__ float gelu_erf_poly(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
-// bf16-output GELU, eight elements in lock-step (independent FMA chains), 13 instructions per element:
+// bf16-output GELU, eight elements in lock-step as four packed fp32x2 lanes (FFMA2 / FMUL2: two fp32 results per
+// issue slot), ~8 instructions per element instead of 13:
 //   erf(|x|/sqrt2) = xc * Q(xc^2), xc = min(|x|, 3.2*sqrt2), Q of degree 8 (minimax fit, |abs err| < 4.3e-5 in
 //   fp32 evaluation — two orders of magnitude below the bf16 rounding of the result), and
 //   gelu(x) = 0.5 x (1 + sign(x) erf(|x|/sqrt2)) = h + |h| * e with h = x/2.
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ void gelu_erf_poly8(float* x) {
-  float xc[8], u[8], q[8];
+  uint64_t xc[4], u[4], q[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    xc[j] = fminf(fabsf(x[j]), 4.525483399593904f);
-    u[j] = xc[j] * xc[j];
-    q[j] = fmaf(u[j], 7.28493733954992e-11f, -7.739619932988917e-09f);
+  for (int j = 0; j < 4; ++j) {
+    xc[j] = pack_f32x2(fminf(fabsf(x[2 * j]), 4.525483399593904f), fminf(fabsf(x[2 * j + 1]), 4.525483399593904f));
+    u[j] = mul_f32x2(xc[j], xc[j]);
+    q[j] = fma_f32x2(u[j], pack_f32x2(7.28493733954992e-11f, 7.28493733954992e-11f),
+                     pack_f32x2(-7.739619932988917e-09f, -7.739619932988917e-09f));
   }
 #define STEGO_POLY_STEP(C) \
-  _Pragma("unroll") for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], u[j], C);
+  _Pragma("unroll") for (int j = 0; j < 4; ++j) q[j] = fma_f32x2(q[j], u[j], pack_f32x2(C, C));
   STEGO_POLY_STEP(3.6041332307651457e-07f)
   STEGO_POLY_STEP(-9.764514095986007e-06f)
   STEGO_POLY_STEP(0.0001730121070631224f)
@@ -61,10 +68,11 @@ __device__ __forceinline__ void gelu_erf_poly8(float* x) {
   STEGO_POLY_STEP(0.7977185244870058f)
 #undef STEGO_POLY_STEP
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float e = q[j] * xc[j];
-    const float h = 0.5f * x[j];
-    x[j] = fmaf(fabsf(h), e, h);
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t e = mul_f32x2(q[j], xc[j]);
+    const float h0 = 0.5f * x[2 * j], h1 = 0.5f * x[2 * j + 1];
+    const uint64_t r = fma_f32x2(pack_f32x2(fabsf(h0), fabsf(h1)), e, pack_f32x2(h0, h1));
+    unpack_f32x2(r, x[2 * j], x[2 * j + 1]);
   }
 }
 

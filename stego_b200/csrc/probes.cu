@@ -8,6 +8,8 @@
 // Both are evaluated per pixel in registers; nothing of size [B, n_classes, H, W] is materialised unless the
 // caller asks for the probabilities.  Dot products are sequential fp32 FMAs in channel order, so the
 // argmax is deterministic; centroids are normalised once per CTA into shared memory.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -336,8 +338,10 @@ linear_ce_kernel(LinearCEParams p) {
   const int bhm = p.box_h, bwm = p.box_w, n = p.n;
   float* slog = sm;                                   // [box_h*box_w][LCE_SLD]
   float* sg = slog + bhm * bwm * LCE_SLD;             // [256][n]   (odd stride n=27: conflict-free)
-  float* sT = sg + 256 * n;                           // [16][box_w][n]
-  float* swx = sT + LCE_TILE * bwm * n;               // [16][box_w]
+  float* sT = sg + 256 * n;                           // [16][box_w][n]  (phase 2)
+  float* sX = sT;                                     // [16][box_h][LCE_SLD] (phase 1: logits interpolated along x) — same region
+  const int region = max(LCE_TILE * bwm * n, LCE_TILE * bhm * LCE_SLD);
+  float* swx = sT + region;                           // [16][box_w]
   float* swy = swx + LCE_TILE * bwm;                  // [16][box_h]
   __shared__ float sred[2][8];
   const int tile = blockIdx.x;
@@ -380,6 +384,17 @@ linear_ce_kernel(LinearCEParams p) {
     swy[t * bhm + (y0 - by0)] += 1.f - ly;
     swy[t * bhm + (y1 - by0)] += ly;
   }
+  // ---- phase 0: interpolate the box along x once per tile column (shared by the 16 pixels of that column):
+  //      sX[x][row][k] = (1 - lx) * L[row][x0][k] + lx * L[row][x1][k]; warps take columns, lanes = classes
+  for (int xc = warp; xc < LCE_TILE; xc += 8) {
+    int x0, x1; float lx;
+    src_index(min(X0 + xc, p.W - 1), sx, p.w, x0, x1, lx);
+    const float* c0 = slog + (x0 - bx0) * LCE_SLD + lane;
+    const float* c1 = slog + (x1 - bx0) * LCE_SLD + lane;
+    for (int row = 0; row < bh; ++row)
+      sX[(xc * bhm + row) * LCE_SLD + lane] = (1.f - lx) * c0[row * bw * LCE_SLD] + lx * c1[row * bw * LCE_SLD];
+  }
+  __syncthreads();
   // ---- phase 1: thread = pixel
   const int py = tid / LCE_TILE, px = tid % LCE_TILE;
   const int Y = Y0 + py, X = X0 + px;
@@ -389,21 +404,18 @@ linear_ce_kernel(LinearCEParams p) {
   const bool valid = inb && lab >= 0 && lab < n;
   float lsum = 0.f, cnt = 0.f;
   {
-    int y0, y1, x0, x1;
-    float ly, lx;
+    int y0, y1;
+    float ly;
     src_index(min(Y, p.H - 1), sy, p.h, y0, y1, ly);
-    src_index(min(X, p.W - 1), sx, p.w, x0, x1, lx);
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const float* l00 = slog + ((y0 - by0) * bw + (x0 - bx0)) * LCE_SLD;
-    const float* l01 = slog + ((y0 - by0) * bw + (x1 - bx0)) * LCE_SLD;
-    const float* l10 = slog + ((y1 - by0) * bw + (x0 - bx0)) * LCE_SLD;
-    const float* l11 = slog + ((y1 - by0) * bw + (x1 - bx0)) * LCE_SLD;
+    const float wy0 = 1.f - ly;
+    const float* r0 = sX + (px * bhm + (y0 - by0)) * LCE_SLD;
+    const float* r1 = sX + (px * bhm + (y1 - by0)) * LCE_SLD;
     float z[LP_LD];
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < LP_LD; ++k) {
       if (k < n) {
-        z[k] = w00 * l00[k] + w01 * l01[k] + w10 * l10[k] + w11 * l11[k];
+        z[k] = fmaf(ly, r1[k], wy0 * r0[k]);
         mx = fmaxf(mx, z[k]);
       }
     }
@@ -414,7 +426,7 @@ linear_ce_kernel(LinearCEParams p) {
     const float inv = 1.0f / se;
     if (valid) {
       const int li = static_cast<int>(lab);
-      const float zl = w00 * l00[li] + w01 * l01[li] + w10 * l10[li] + w11 * l11[li];  // dynamic smem index
+      const float zl = fmaf(ly, r1[li], wy0 * r0[li]);  // dynamic smem index
       lsum = __logf(se) - (zl - mx);  // lse - z_lab
       cnt = 1.f;
     }
@@ -635,7 +647,8 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   p.box_w = (int)((double)LCE_TILE * w / Wimg) + 3;
   if (p.box_h > h) p.box_h = h;
   if (p.box_w > w) p.box_w = w;
-  const size_t ce_smem = ((size_t)p.box_h * p.box_w * LCE_SLD + 256 * (size_t)n_classes + (size_t)LCE_TILE * p.box_w * n_classes +
+  const size_t region = std::max((size_t)LCE_TILE * p.box_w * n_classes, (size_t)LCE_TILE * p.box_h * LCE_SLD);
+  const size_t ce_smem = ((size_t)p.box_h * p.box_w * LCE_SLD + 256 * (size_t)n_classes + region +
                           (size_t)LCE_TILE * (p.box_w + p.box_h)) * sizeof(float);
   STEGO_CHECK_ARG(ce_smem <= 200 * 1024, "stego_linear_probe_ce: upsample ratio %dx%d -> %dx%d needs %zu B of smem", h, w, H, Wimg, ce_smem);
   {
