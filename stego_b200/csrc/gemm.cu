@@ -60,7 +60,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // BN = 128 / 256: two accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1).
   // BN = 384 (a whole E = 384 row block per CTA: A is read ONCE instead of three times): one 384-column
   // accumulator (TMEM has 512 columns), two MMAs per k-step (N = 256 + 128), single epilogue staging tile.
-  static_assert(BN == 128 || BN == 256 || BN == 384, "BN must be 128, 256 or 384");
+  static_assert(BN == 128 || BN == 192 || BN == 256 || BN == 384, "BN must be 128, 192, 256 or 384");
   constexpr uint32_t kAccBufs = (BN == 384) ? 1u : 2u;
   constexpr int kEpiWarps = gemm_epi_warps(BN);
   constexpr int kParts = kEpiWarps / 4;      // warps sharing one TMEM lane quarter
@@ -72,8 +72,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(BN != 384 || (!A_MN && !B_MN), "384-wide tiles are K-major only");
   // kCluster: two CTAs (a thread-block cluster) work on two M-adjacent tiles of the same N block; each loads its own
   // A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> B traffic from L2 is halved.
-  static_assert(!kCluster || (!A_MN && !B_MN && BN != 384), "cluster multicast: K-major 128/256 tiles only");
+  static_assert(!kCluster || (!A_MN && !B_MN && BN != 384 && BN != 192), "cluster multicast: K-major 128/256 tiles only");
+  static_assert(BN != 192 || (!A_MN && !B_MN), "192-wide tiles are K-major only");
   constexpr uint32_t B_BOX_ROWS = kCluster ? (BN / 2) : 128;  // rows of one B TMA box (tensor map built to match)
+  constexpr int kBBox = (BN % 128 == 0) ? 128 : 64;           // non-cluster K-major B box rows (192 = 3 x 64)
   const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,8 +157,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                   tn * BN + crank * B_BOX_ROWS, 0x3);
           } else if (!B_MN) {
 #pragma unroll
-            for (int blk = 0; blk < BN / 128; ++blk)  // tensor-map box = 128 rows
-              tma_load_2d(sb + blk * 16384, &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * 128);
+            for (int blk = 0; blk < BN / kBBox; ++blk)  // tensor-map box = kBBox rows
+              tma_load_2d(sb + blk * (kBBox * 128), &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * kBBox);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / 64; ++blk)
@@ -557,7 +559,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
                (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
                !(out_bf16 && residual != nullptr);
   // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
-  const bool wide = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
+  const bool wide_n = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
   // 2-CTA clusters with TMA multicast of the shared B tile (K-major, no split-K, enough M tiles to pair up)
   static int cluster_opt = -1, prefetch_opt = 0, two_cta_opt = 0;
   if (cluster_opt < 0) {
@@ -573,7 +575,17 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     const char* e = getenv("STEGO_GEMM_DIAG");  // read every call: bench.py toggles it between diagnostic timings
     p.diag = e ? atoi(e) : 0;
   }
-  const bool use_384 = !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
+  static int bn192_opt = -1;
+  if (bn192_opt < 0) {
+    const char* e = getenv("STEGO_GEMM_BN192");
+    bn192_opt = e ? atoi(e) : 0;
+  }
+  // 128 x 192 tiles (two accumulator buffers, 4 stages): N = 384 as two tiles whose epilogue overlaps the next
+  // mainloop (the 128 x 384 tile has a single accumulator); bit 1: N = 384/768 residual GEMMs, bit 2: also N = 1152 (qkv)
+  const bool use_192 = !a_mn_major && !b_mn_major && splits == 1 && N % 192 == 0 &&
+                       (((bn192_opt & 1) && N <= 768 && K >= 1024) || ((bn192_opt & 2) && N == 1152));
+  const bool wide = wide_n && !use_192;
+  const bool use_384 = !use_192 && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
   const bool cluster = cluster_opt && !a_mn_major && !b_mn_major && splits == 1 && !atomic_out && M >= 512 && !use_384;
 
   // TMA epilogue: plain store for outputs without a residual; fp32 reduce-add when the residual IS the output
@@ -600,7 +612,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   {
     uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, b_mn_major ? 64u : ((cluster && !wide) ? 64u : 128u)};
+    uint32_t box[2] = {64, b_mn_major ? 64u : (((cluster && !wide) || use_192) ? 64u : 128u)};
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
   if (p.tma_epi) {
@@ -614,6 +626,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   }
   // N == 384 (ViT-S proj / fc2, in-place residual): one 128 x 384 tile per CTA reads each A row block once
   // (only worth it when the mainloop dominates: the single accumulator cannot overlap epilogue and MMAs)
+  if (p.tma_epi && use_192) return launch_gemm<192, 4, false, false>(tmA, tmB, tmO, p, stream);
   if (p.tma_epi && use_384) return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (cluster && !(p.tma_epi == 0 && use_384)) {
     if (wide) return launch_gemm<256, 3, false, false, true>(tmA, tmB, tmO, p, stream);
