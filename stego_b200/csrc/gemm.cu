@@ -578,7 +578,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   static int bn192_opt = -1;
   if (bn192_opt < 0) {
     const char* e = getenv("STEGO_GEMM_BN192");
-    bn192_opt = e ? atoi(e) : 0;
+    bn192_opt = e ? atoi(e) : 2;  // default: qkv only (6 exact tiles instead of 4.5 of 256: 56.6 -> 54.6 us); fc2 measured no gain
   }
   // 128 x 192 tiles (two accumulator buffers, 4 stages): N = 384 as two tiles whose epilogue overlaps the next
   // mainloop (the 128 x 384 tile has a single accumulator); bit 1: N = 384/768 residual GEMMs, bit 2: also N = 1152 (qkv)
