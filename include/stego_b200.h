@@ -194,6 +194,18 @@ STEGO_API int stego_eval_probes(const float* code, long long ld_code, int C, int
                                 float* clu_log_probs, unsigned char* lin_argmax, unsigned char* clu_argmax,
                                 void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * k-nearest-neighbour descriptors (src/precompute_knns.py:15-21, 83-96):
+ *   normed = F.normalize(feats, dim=1);  sims = einsum("nf,mf->nm", normed, normed);  idx = topk(sims, k)[1]
+ * fused: the [n][n] similarity matrix is never materialised (tcgen05 tiles in TMEM, bf16 hi/lo split = 3 passes,
+ * per-row running top-k in the epilogue).  feats: fp32 [n][E] (un-normalised, e.g. GAP-pooled ViT features),
+ * E a multiple of 64, 1 <= k <= 32.  planes_scratch: 2*n*E bf16 (16-byte aligned).  idx_out: int64 [n][k], sorted by
+ * descending similarity (ties: lower index first; a row is its own nearest neighbour, as in the reference);
+ * val_out: optional fp32 [n][k] similarities.
+ * ---------------------------------------------------------------------------------------------- */
+STEGO_API int stego_knn_topk(const float* feats, int n, int E, int k, void* planes_scratch, long long* idx_out,
+                             float* val_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

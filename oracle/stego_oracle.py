@@ -379,3 +379,26 @@ def training_losses(image_feat: Tensor, image_feat_pos: Tensor, hp: Dict[str, Te
     return dict(total=corr + lin + clu, corr=corr, linear=lin, cluster=clu,
                 pos_intra=out6[0], pos_inter=out6[2], neg_inter=out6[4].mean(),
                 cd_intra=out6[1].mean(), cd_inter=out6[3].mean(), cd_neg=out6[5].mean(), code=code)
+
+
+# --------------------------------------------------------------------------------------------------
+# kNN descriptors — src/precompute_knns.py
+# --------------------------------------------------------------------------------------------------
+def knn_descriptors(image_feat: Tensor) -> Tensor:
+    """precompute_knns.py:19 (get_feats): global-average-pool the [B,E,h,w] feature map, then L2-normalise."""
+    return F.normalize(image_feat.mean([2, 3]), dim=1)
+
+
+def knn_indices(normed_feats: Tensor, k: int = 30, n_batches: int = 16) -> Tuple[Tensor, Tensor]:
+    """precompute_knns.py:83-92: similarities of every descriptor against all of them in n_batches slabs
+    (`einsum("nf,mf->nm")`), `torch.topk(sims, k)` indices (each row contains itself).  Also returns the similarities
+    (the reference discards them) so that tests can compare rankings up to floating-point ties."""
+    n = normed_feats.shape[0]
+    step = max(1, n // n_batches)
+    idx, val = [], []
+    for i in range(0, n, step):
+        sims = torch.einsum("nf,mf->nm", normed_feats[i:i + step], normed_feats)
+        v, ix = torch.topk(sims, k)
+        idx.append(ix)
+        val.append(v)
+    return torch.cat(idx, 0), torch.cat(val, 0)
