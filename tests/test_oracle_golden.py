@@ -114,3 +114,19 @@ def test_clamp_gradient_is_inclusive():
 def test_oracle_matches_real_reference():
     import check_against_reference
     assert check_against_reference.run_checks()
+
+
+def test_knn_oracle_against_brute_force():
+    """oracle.knn_descriptors / knn_indices (restating src/precompute_knns.py:19, 83-92) against an independent
+    argsort of the full similarity matrix; row i must list itself first (cosine similarity 1)."""
+    g = torch.Generator().manual_seed(5)
+    fmap = torch.randn(97, 64, 4, 4, generator=g)
+    d = O.knn_descriptors(fmap)
+    assert torch.allclose(d.norm(dim=1), torch.ones(97), atol=1e-6)
+    assert torch.allclose(d, torch.nn.functional.normalize(fmap.mean([2, 3]), dim=1))
+    idx, val = O.knn_indices(d, 10, n_batches=16)
+    sims = d @ d.t()
+    order = torch.argsort(sims, dim=1, descending=True, stable=True)[:, :10]
+    assert (idx[:, 0] == torch.arange(97)).all()
+    assert torch.equal(idx, order)
+    assert torch.allclose(val, sims.gather(1, order))
