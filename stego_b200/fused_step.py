@@ -252,7 +252,7 @@ class FusedStep:
         if seg._flat is None:
             seg.configure_optimizers()
         net_optim, linear_probe_optim, cluster_probe_optim = seg.optimizers()
-        key = (B, H, W, LH, LW, dev.index)
+        key = (B, H, W, LH, LW, dev.index, id(seg._flat))  # a new flat parameter buffer invalidates the captured graph
         if self.key != key:
             self.ws = self._alloc(B, H, W, LH, LW, dev)
             self.key = key
