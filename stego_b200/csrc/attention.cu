@@ -7,8 +7,10 @@
 // P (bf16) goes through swizzled shared memory straight back into the tensor core for P V.
 //
 // One CTA per (128-query tile, head, image), head_dim = 64, 320 threads:
-//   warp 0      TMA producer: Q tile once, then a 3-stage ring of (K,V) tiles
-//   warp 1      MMA issuer  : S_j = Q K_j^T (128x128x64), O_j = P_j V_j (128x64x128)
+//   warp 0      TMA producer: Q tile and the first K/V stages before the CTA-wide sync, then a 4-stage ring of
+//               64-key (K,V) tiles
+//   warp 1      MMA issuer (whole warp in uniform control flow, one elected lane): S_j = Q K_j^T (128x64x64) two
+//               tiles ahead of O += P_j V_j (128x64x64)
 //   warps 2..5  softmax warpgroup 0  (KV tiles 0,2,4,..)   } each thread owns one query row, keeps its own
 //   warps 6..9  softmax warpgroup 1  (KV tiles 1,3,5,..)   } reference max / running sum
 // O accumulates IN TMEM across a warpgroup's KV tiles (tcgen05.mma accumulate), so the softmax warps never wait
@@ -16,7 +18,9 @@
 // new row max exceeds it by more than 2^8, and only then is O rescaled in TMEM (tcgen05.ld -> scale ->
 // tcgen05.st); otherwise P = exp2(s - m_ref) is at most 256, harmless in bf16 / fp32.
 // The two warpgroups work on alternate KV tiles (S, P, O are double buffered) and are merged once at the
-// end (split-KV combine), so there is no cross-warpgroup dependency inside the loop.
+// end (split-KV combine, both accumulators read straight from TMEM), so there is no cross-warpgroup dependency inside
+// the loop; the [128 x 64] output tile is staged in the idle P tile and leaves as two TMA bulk stores.
+// Two CTAs per SM (112 KB of shared memory, 256 TMEM columns each).
 // Input is the packed qkv GEMM output [B, N, 3E] bf16 (q | k | v, head-major inside each), read through
 // ONE 3-D tensor map; rows past N (ragged last tile: N = hw + 1 is never a multiple of 128) are
 // zero-filled by TMA and masked to -inf in the softmax.
