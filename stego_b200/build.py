@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include"),
-]
+] + os.environ.get("STEGO_NVCC_DEFS", "").split()  # e.g. -DSTEGO_ATT_TRACE for profiles/attn_trace.py (diagnostic build)
 
 
 def _sources():

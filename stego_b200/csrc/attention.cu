@@ -48,7 +48,24 @@ constexpr uint32_t ATT_SMEM_ML = ATT_SMEM_Q;  // m,l of WG1 (2 x 128 floats) reu
 constexpr uint32_t ATT_SMEM_BAR = ATT_SMEM_P + 2 * ATT_P_BYTES;
 constexpr uint32_t ATT_SMEM_TOTAL = ATT_SMEM_BAR + 256;  // 112.25 KB: two CTAs per SM (<= 113 KB each)
 
+// Diagnostic build only (-DSTEGO_ATT_TRACE, see profiles/attn_trace.py): lane 0 of every warp of a few CTAs stamps
+// (globaltimer, event id) pairs into a global buffer so the pipeline of one CTA can be drawn as a timeline.  The
+// default build contains none of this.
+#ifdef STEGO_ATT_TRACE
+constexpr int ATT_TRACE_EVENTS = 256;   // per warp
+constexpr int ATT_TRACE_SLOTS = 8;      // traced CTAs
+static unsigned long long* g_att_trace = nullptr;
+static int g_att_trace_every = 0;
+#define ATT_TRACE(ev) att_trace_event(p, warp, lane, (ev), trace_seq)
+#else
+#define ATT_TRACE(ev) ((void)0)
+#endif
+
 struct AttnParams {
+#ifdef STEGO_ATT_TRACE
+  unsigned long long* trace;  // [SLOTS][10 warps][EVENTS][2]
+  int trace_every;            // CTA with linear id i is traced into slot i / every if i % every == 0
+#endif
   bf16* out;   // [B*N][E] bf16 (heads concatenated, like .transpose(1,2).reshape(B,N,C))
   int N;       // tokens per image
   int E;       // embed dim = heads * 64
@@ -57,6 +74,20 @@ struct AttnParams {
   int diag;           // STEGO_ATT_DIAG phase-timing flags (results garbage): 1 skip softmax math, 2 skip MMAs, 4 skip TMA,
                       // 8 no KV tiles at all (prologue + merge + store only), 16 skip the output stores
 };
+
+#ifdef STEGO_ATT_TRACE
+__device__ __forceinline__ void att_trace_event(const AttnParams& p, int warp, int lane, int ev, int& seq) {
+  if (lane != 0 || p.trace == nullptr || p.trace_every <= 0) return;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (cta % p.trace_every != 0) return;
+  const int slot = cta / p.trace_every;
+  if (slot >= ATT_TRACE_SLOTS || seq >= ATT_TRACE_EVENTS) return;
+  unsigned long long* e = p.trace + ((static_cast<size_t>(slot) * 10 + warp) * ATT_TRACE_EVENTS + seq) * 2;
+  e[0] = globaltimer_ns();
+  e[1] = static_cast<unsigned long long>(ev) | (static_cast<unsigned long long>(cta) << 32);
+  ++seq;
+}
+#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, AttnParams p) {
@@ -76,6 +107,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef STEGO_ATT_TRACE
+  int trace_seq = 0;
+#endif
+  ATT_TRACE(1);  // CTA start
   const int q0 = blockIdx.x * ATT_BQ;
   const int head = blockIdx.y;
   const int img = blockIdx.z;
@@ -115,6 +150,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ATT_TRACE(2);  // prologue done (barriers, TMEM, CTA-wide sync)
   const uint32_t TM_S = tmem_base;         // S[b] at + b*64
   const uint32_t TM_O = tmem_base + 128;   // O[b] at + b*64
 
@@ -129,6 +165,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
         tma_load_3d(sk, &tmQKV, &kv_full[stage], p.E + head * ATT_D, j * ATT_BKV, img);
         tma_load_3d(sv, &tmQKV, &kv_full[stage], 2 * p.E + head * ATT_D, j * ATT_BKV, img);
+        ATT_TRACE(140 + j);  // K/V tile j requested
         if (++stage == ATT_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -165,6 +202,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         umma_commit(&kv_empty[stage_i]);  // K_i and V_i are no longer needed
       }
       __syncwarp();
+      ATT_TRACE(40 + i);  // P_i V_i issued
     };
     // S runs two tiles ahead of P V: the S buffer of tile j+2 is free as soon as the softmax warpgroup holds the
     // scores of tile j in registers (early s_empty), so S_{j+2} is issued BEFORE the blocking wait for P_j and is
@@ -187,6 +225,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         umma_commit(&s_full[b]);
       }
       __syncwarp();
+      ATT_TRACE(10 + j);  // S_j issued
     };
     const int ahead = p.s_ahead;
     for (int j = 0; j < ahead && j < nkv; ++j) issue_s(j);
@@ -211,6 +250,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const int valid = p.N - j * ATT_BKV;  // number of real keys in this tile (>= 1)
       mbar_wait(&s_full[wg], it & 1u);
       tc_fence_after();
+      ATT_TRACE(70 + j);  // S_j visible to this warp
       if (!warp_has_rows || (p.diag & 1)) {
         // ragged last query tile (N = hw + 1): this warp's 32 rows are all padding — keep the barrier protocol,
         // skip the loads / exponentials / stores (their P rows and O rows are never read back)
@@ -327,7 +367,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
+      ATT_TRACE(100 + j);  // P_j stored, p_full signalled
     }
+    ATT_TRACE(130);  // KV loop done
     // ---- combine the two warpgroups (split-KV merge) and write the output ----
     // Both O accumulators live in the SAME TMEM lanes (rows), 64 columns apart, so warpgroup 0 reads both
     // straight out of TMEM; only m and l of warpgroup 1 travel through shared memory.
@@ -393,6 +435,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
   }
 
+  ATT_TRACE(131);  // role finished (merge + store done for warpgroup 0)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -441,6 +484,10 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
       ahead = (e && e[0] == '1') ? 1 : 2;
     }
     p.s_ahead = ahead;
+#ifdef STEGO_ATT_TRACE
+    p.trace = g_att_trace;
+    p.trace_every = g_att_trace_every;
+#endif
     const char* dg = getenv("STEGO_ATT_DIAG");  // read every call (profiles/attn_phases.py toggles it)
     p.diag = dg ? atoi(dg) : 0;
   }
@@ -449,3 +496,12 @@ extern "C" int stego_attention_fwd(const void* qkv, void* out, int B, int N, int
   STEGO_CHECK_LAUNCH("attention_fwd_kernel");
   return STEGO_OK;
 }
+
+#ifdef STEGO_ATT_TRACE
+// Diagnostic build only: buffer of ATT_TRACE_SLOTS * 10 * ATT_TRACE_EVENTS * 2 u64 (zero it first); every-th CTA is traced.
+extern "C" int stego_attention_set_trace(unsigned long long* buf, int every) {
+  g_att_trace = buf;
+  g_att_trace_every = every;
+  return STEGO_OK;
+}
+#endif
