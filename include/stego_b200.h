@@ -53,22 +53,15 @@ STEGO_API int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void
                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
                               void* stream);
 
-/* Fused residual GEMM + LayerNorm of a pre-norm transformer block (src/dino/vision_transformer.py:92-104,
- * Block.forward:  x = x + proj(attn(...)) ; norm2(x)   and   x = x + fc2(...) ; next block's norm1(x)):
- *     x[M][ldx] (fp32, in place) += A[M][lda] . W[N][ldw]^T + bias ;   y[M][ldy] (bf16) = LN(x) * gamma + beta
- * with biased variance and `eps` inside the square root like nn.LayerNorm.  One CTA holds a whole output row in
- * TMEM, so N must be 384 (ViT-S/8 embed dim) — other widths return STEGO_ERR_UNSUPPORTED and the caller uses
- * stego_gemm_bf16 + stego_layernorm_bf16.  All pointers 16-byte aligned; K tail zero-filled by TMA. */
-STEGO_API int stego_gemm_residual_ln_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
-                                          float* x, int ldx, const float* bias, const float* gamma,
-                                          const float* beta, float eps, void* y, int ldy, void* stream);
-
 /* ------------------------------------------------------------------------------------------------
  * Frozen DINO ViT forward pieces (reference: src/dino/vision_transformer.py)
  * ---------------------------------------------------------------------------------------------- */
 /* PatchEmbed conv (:127-131) as im2col: img [B][3][H][W] fp32 -> rows [B*(H/p)*(W/p)][3*p*p] bf16,
  * column order = flattening of the conv weight [E][3][p][p]. */
 STEGO_API int stego_vit_patchify(const float* img, void* out_bf16, int B, int H, int W, int patch, void* stream);
+/* Same, for an image batch already held in bf16 (the precision the fp32 variant rounds to): half the input bytes. */
+STEGO_API int stego_vit_patchify_bf16(const void* img_bf16, void* out_bf16, int B, int H, int W, int patch,
+                                      void* stream);
 /* prepare_tokens (:203-207): x[b][0][:] = cls_token + pos_embed[0] (fp32 residual stream [B][ntok][E]). */
 STEGO_API int stego_vit_cls_rows(float* x, const float* cls_token, const float* pos_embed, int B, int ntok, int E,
                                  void* stream);
@@ -171,12 +164,14 @@ STEGO_API int stego_cluster_lookup_bwd(const float* x, long long stride_b, long 
                                        float* dnc_scratch, float* dclusters, void* stream);
 /* Linear probe step (src/train_segmentation.py:213-218): 1x1 conv on tokens-major code [B*h*w][ld_code],
  * bilinear upsample to [H][W] (align_corners=False), CrossEntropyLoss over pixels with 0 <= label < n.
+ * label [B][H][W]: int64 (the reference's dtype), int32 or uint8 — label_bytes = 8 / 4 / 1; labels outside [0, n)
+ * are ignored (-1 in the signed types, 255 in uint8: the same mask as src/train_segmentation.py:211).
  * loss_out[0] = mean CE, loss_out[1] = valid pixel count.  If dlogits_scratch is non-null (zeroed by the
  * caller) the backward also runs: dW [n][C] and db [n] += grad_loss * gradient.
  * logits_scratch / dlogits_scratch: [B*h*w][32] floats; partials_scratch: >= 16*SMs floats. */
 STEGO_API int stego_linear_probe_ce(const float* code, long long ld_code, int C, const float* W, const float* bias,
-                                    int n_classes, const long long* label, int B, int h, int w, int H, int Wimg,
-                                    float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
+                                    int n_classes, const void* label, int label_bytes, int B, int h, int w, int H,
+                                    int Wimg, float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
                                     float* loss_out, float grad_loss, float* dW, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -34,17 +34,6 @@ if "fc1" in which:
     gemm(4 * E, E, act=1)
 if "fc2" in which:
     gemm(E, 4 * E, residual=True)
-if "projln" in which or "fc2ln" in which:
-    for name, K in (("projln", E), ("fc2ln", 4 * E)):
-        if name not in which:
-            continue
-        a = torch.randn(M, K, device=dev).bfloat16()
-        w = (torch.randn(E, K, device=dev) * K ** -0.5).bfloat16()
-        x = torch.randn(M, E, device=dev)
-        y = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
-        g = torch.ones(E, device=dev)
-        for _ in range(2):
-            ops.gemm_residual_ln(a, w, x, g, g, g, y)
 if "attn" in which:
     qkv = torch.randn(M, 3 * E, device=dev).bfloat16()
     ao = torch.empty(M, E, device=dev, dtype=torch.bfloat16)

@@ -1,4 +1,4 @@
-// Activation helpers shared by the GEMM epilogues (gemm.cu, gemm_2cta.cu).
+// Activation helpers shared by the GEMM epilogues (gemm.cu).
 #pragma once
 #include "common.cuh"
 

@@ -29,6 +29,14 @@ constexpr int GEMM_BK = 64;
 __host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN == 384 ? 8 : 8; }
 __host__ __device__ constexpr int gemm_threads(int BN) { return 64 + 32 * gemm_epi_warps(BN); }
 
+// Phase-isolation switches (profiles/gemm_phases.py) exist only in a -DSTEGO_DIAG build; the default build folds them
+// to constants (no getenv on the launch path, no diag branches in the kernel).
+#ifdef STEGO_DIAG
+#define GEMM_DIAG(p, bit) (((p).diag & (bit)) != 0)
+#else
+#define GEMM_DIAG(p, bit) false
+#endif
+
 struct GemmParams {
   int M, N, K;        // logical GEMM sizes; K is the reduction length
   int splits;         // split-K factor (>=1); every split owns >= 1 k-block
@@ -45,12 +53,11 @@ struct GemmParams {
   int vec_ok;         // host-verified 16-byte alignment of out/residual rows
   int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
   int tma_epi;        // 1: epilogue tiles leave through TMA stores; 2: TMA fp32 reduce-add (in-place residual)
-  int l2_prefetch;    // producer prefetches the A row block of its NEXT tile into L2 (first touch comes from HBM)
-  int diag;           // STEGO_GEMM_DIAG bit flags for phase timing ONLY (results are garbage): 1 skip the epilogue work,
-                      // 2 skip the MMAs, 4 skip the TMA loads
+  int diag;           // -DSTEGO_DIAG builds only: STEGO_GEMM_DIAG bit flags for phase timing (results are garbage):
+                      // 1 skip the epilogue work, 2 skip the MMAs, 4 skip the TMA loads
 };
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster>
+template <int BN, int kStages, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, GemmParams p) {
@@ -70,13 +77,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, N0, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
   constexpr uint32_t IDESC_TAIL = make_idesc_bf16(GEMM_BM, 128, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
   static_assert(BN != 384 || (!A_MN && !B_MN), "384-wide tiles are K-major only");
-  // kCluster: two CTAs (a thread-block cluster) work on two M-adjacent tiles of the same N block; each loads its own
-  // A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> B traffic from L2 is halved.
-  static_assert(!kCluster || (!A_MN && !B_MN && BN != 384 && BN != 192), "cluster multicast: K-major 128/256 tiles only");
   static_assert(BN != 192 || (!A_MN && !B_MN), "192-wide tiles are K-major only");
-  constexpr uint32_t B_BOX_ROWS = kCluster ? (BN / 2) : 128;  // rows of one B TMA box (tensor map built to match)
   constexpr int kBBox = (BN % 128 == 0) ? 128 : 64;           // non-cluster K-major B box rows (192 = 3 x 64)
-  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,13 +94,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   const int tiles_m_real = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int tiles_m = kCluster ? ((tiles_m_real + 1) & ~1) : tiles_m_real;  // cluster: pairs of M tiles (last may be OOB)
+  const int tiles_m = tiles_m_real;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;  // K tail: TMA zero-fills out-of-bounds
-  // cluster mode: the scheduler walks PAIRS; both CTAs of a cluster see the same pair sequence
-  const int total_tiles = kCluster ? (tiles_m / 2) * tiles_n : tiles_m * tiles_n * p.splits;
-  const int sched_start = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int sched_step = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_tiles = tiles_m * tiles_n * p.splits;
+  const int sched_start = static_cast<int>(blockIdx.x);
+  const int sched_step = static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -106,7 +107,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tma_epi) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kCluster ? 2 : 1);  // cluster: both CTAs' MMAs must release a stage
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -117,28 +118,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && !(p.diag & 4)) {
+    if (lane == 0 && !GEMM_DIAG(p, 4)) {
       uint32_t stage = 0, phase = 0;
       for (int t = sched_start; t < total_tiles; t += sched_step) {
-        const int split = kCluster ? 0 : t % p.splits;
-        const int tn = kCluster ? t % tiles_n : (t / p.splits) % tiles_n;
-        const int tm = kCluster ? (t / tiles_n) * 2 + static_cast<int>(crank) : t / (p.splits * tiles_n);
+        const int split = t % p.splits;
+        const int tn = (t / p.splits) % tiles_n;
+        const int tm = t / (p.splits * tiles_n);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
-        if (!A_MN && !kCluster && p.l2_prefetch) {
-          const int t2 = t + sched_step;
-          if (t2 < total_tiles) {
-            const int tm2 = t2 / (p.splits * tiles_n);
-            if (tm2 != tm)
-              for (int kb = kb0; kb < kb1; ++kb) tma_prefetch_l2_2d(&tmA, kb * GEMM_BK, tm2 * GEMM_BM);
-          }
-        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -151,11 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int blk = 0; blk < GEMM_BM / 64; ++blk)
               tma_load_2d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK);
           }
-          if (kCluster) {
-            // this CTA's half of the B tile, delivered to both CTAs (and counted on both full barriers)
-            tma_load_2d_multicast(sb + crank * (B_BOX_ROWS * 128), &tmB, &full_bar[stage], kb * GEMM_BK,
-                                  tn * BN + crank * B_BOX_ROWS, 0x3);
-          } else if (!B_MN) {
+          if (!B_MN) {
 #pragma unroll
             for (int blk = 0; blk < BN / kBBox; ++blk)  // tensor-map box = kBBox rows
               tma_load_2d(sb + blk * (kBBox * 128), &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * kBBox);
@@ -183,28 +171,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? 8192u : 16u);
     const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192u : 16u);
     for (int t = sched_start; t < total_tiles; t += sched_step) {
-      const int split = kCluster ? 0 : t % p.splits;
+      const int split = t % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(num_kb, kb0 + p.kb_per_split);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + acc * (TMEM_COLS / kAccBufs);
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (!(p.diag & 4)) mbar_wait(&full_bar[stage], phase);
+        if (!GEMM_DIAG(p, 4)) mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
         const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t k = 0; k < ((p.diag & 2) ? 0u : GEMM_BK / 16); ++k) {
+          for (uint32_t k = 0; k < (GEMM_DIAG(p, 2) ? 0u : GEMM_BK / 16); ++k) {
             const uint64_t da = smem_desc_join(a_lo + k * A_KSTEP, DESC_HI);
             umma_bf16(tmem_d, da, smem_desc_join(b_lo + k * B_KSTEP, DESC_HI), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             if (BN == 384)  // columns 256..383 of the accumulator <- B rows 256..383
               umma_bf16(tmem_d + 256, da, smem_desc_join(b_lo + ((256u * 128u) >> 4) + k * B_KSTEP, DESC_HI), IDESC_TAIL,
                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (kCluster) umma_commit_multicast(&empty_bar[stage], 0x3);  // release the stage in BOTH CTAs
-          else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -220,8 +207,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     uint32_t epi_groups = 0;  // bulk-store groups this warp has committed (selects the staging tile)
     for (int t = sched_start; t < total_tiles; t += sched_step) {
-      const int tn = kCluster ? t % tiles_n : (t / p.splits) % tiles_n;
-      const int tm = kCluster ? (t / tiles_n) * 2 + static_cast<int>(crank) : t / (p.splits * tiles_n);
+      const int tn = (t / p.splits) % tiles_n;
+      const int tm = t / (p.splits * tiles_n);
       if (p.fast_epi && !p.tma_epi && p.residual != nullptr) {
         // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
         const int prow = tm * GEMM_BM + quarter * 32 + lane;
@@ -235,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (p.diag & 1) {
+      if (GEMM_DIAG(p, 1)) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -469,19 +456,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (p.tma_epi && warp >= 2 && lane == 0) tma_wait_group_read<0>();  // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // neither CTA may exit while the peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool kCluster = false>
+template <int BN, int kStages, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        cudaStream_t stream) {
   constexpr size_t smem = size_t(kStages) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + gemm_epi_warps(BN) * (BN == 384 ? 1 : 2) * 4096 + 1024 + 256;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, kCluster>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -490,27 +476,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  if (kCluster) {
-    const int pairs = ((tiles_m + 1) / 2) * tiles_n;
-    int clusters = num_sms() / 2;
-    if (pairs < clusters) clusters = pairs;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(gemm_threads(BN));
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm cluster)");
-    count_launch();
-    return STEGO_OK;
-  }
   const int tiles = tiles_m * tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, gemm_threads(BN), smem, stream>>>(tmA, tmB, tmO, p);
@@ -521,10 +486,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }  // namespace stego
 
 using namespace stego;
-
-// gemm_2cta.cu: cta_group::2 kernel for the wide K-major linears
-int stego_launch_gemm_2cta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* out, int ldo,
-                           int out_bf16, const float* bias, int act, int reduce_add, cudaStream_t stream);
 
 // C-ABI: see include/stego_b200.h for the contract.
 extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
@@ -558,36 +519,6 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   p.fast_epi = p.vec_ok && !atomic_out && row_div == 0 && (N % 32 == 0) &&
                (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
                !(out_bf16 && residual != nullptr);
-  // wide tiles (128 x 256) halve the A re-reads from L2 for the wide-N linears (qkv, fc1)
-  const bool wide_n = !a_mn_major && !b_mn_major && N >= 1024 && splits == 1;
-  // 2-CTA clusters with TMA multicast of the shared B tile (K-major, no split-K, enough M tiles to pair up)
-  static int cluster_opt = -1, prefetch_opt = 0, two_cta_opt = 0;
-  if (cluster_opt < 0) {
-    const char* e = getenv("STEGO_GEMM_CLUSTER");
-    cluster_opt = e ? atoi(e) : 0;
-    e = getenv("STEGO_GEMM_PREFETCH");
-    prefetch_opt = e ? atoi(e) : 0;
-    e = getenv("STEGO_GEMM_2CTA");
-    two_cta_opt = e ? atoi(e) : 0;
-  }
-  p.l2_prefetch = prefetch_opt;
-  {
-    const char* e = getenv("STEGO_GEMM_DIAG");  // read every call: bench.py toggles it between diagnostic timings
-    p.diag = e ? atoi(e) : 0;
-  }
-  static int bn192_opt = -1;
-  if (bn192_opt < 0) {
-    const char* e = getenv("STEGO_GEMM_BN192");
-    bn192_opt = e ? atoi(e) : 2;  // default: qkv only (6 exact tiles instead of 4.5 of 256: 56.6 -> 54.6 us); fc2 measured no gain
-  }
-  // 128 x 192 tiles (two accumulator buffers, 4 stages): N = 384 as two tiles whose epilogue overlaps the next
-  // mainloop (the 128 x 384 tile has a single accumulator); bit 1: N = 384/768 residual GEMMs, bit 2: also N = 1152 (qkv)
-  const bool use_192 = !a_mn_major && !b_mn_major && splits == 1 && N % 192 == 0 &&
-                       (((bn192_opt & 1) && N <= 768 && K >= 1024) || ((bn192_opt & 2) && N == 1152));
-  const bool wide = wide_n && !use_192;
-  const bool use_384 = !use_192 && !a_mn_major && !b_mn_major && N % 384 == 0 && N <= 768 && K >= 1024 && splits == 1;
-  const bool cluster = cluster_opt && !a_mn_major && !b_mn_major && splits == 1 && !atomic_out && M >= 512 && !use_384;
-
   // TMA epilogue: plain store for outputs without a residual; fp32 reduce-add when the residual IS the output
   // (the in-place x += ... of the transformer blocks) — then the epilogue issues no global loads at all.
   p.tma_epi = 0;
@@ -595,10 +526,23 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     if (residual == nullptr) p.tma_epi = 1;
     else if (!out_bf16 && residual == out && ldr == ldo) p.tma_epi = 2;
   }
-
-  // wide K-major linears (qkv, fc1): CTA pairs with UMMA M = 256, each CTA stages only half of the B tile
-  if (two_cta_opt && wide && p.tma_epi && M >= 256 && lda % 8 == 0)
-    return stego_launch_gemm_2cta(A, lda, B, ldb, M, N, K, out, ldo, out_bf16, bias, act, p.tma_epi == 2, stream);
+  p.diag = 0;
+#ifdef STEGO_DIAG
+  {
+    const char* e = getenv("STEGO_GEMM_DIAG");  // read every call: profiles/gemm_phases.py toggles it between timings
+    p.diag = e ? atoi(e) : 0;
+  }
+#endif
+  // Tile shape (the kernel launched below fixes the B box of the tensor map, so it is decided first):
+  //   128 x 256  wide-N linears (fc1: N >= 1024): halves the A re-reads from L2
+  //   128 x 192  N = 1152 (qkv): six exact tiles instead of 4.5 of 256; two accumulator buffers, 4 stages
+  //   128 x 384  N = 384 / 768 with K >= 1024 (fc2): each A row block is read once; single accumulator
+  //   128 x 128  everything else (incl. MN-major operands, split-K, non-TMA epilogues)
+  // The 192 / 384 kernels only exist with the TMA epilogue; anything else falls back to 128-wide tiles.
+  const bool k_major = !a_mn_major && !b_mn_major && splits == 1;
+  const bool use_192 = k_major && p.tma_epi && N == 1152;
+  const bool use_384 = k_major && p.tma_epi && !use_192 && N % 384 == 0 && N <= 768 && K >= 1024;
+  const bool wide = k_major && !use_192 && !use_384 && N >= 1024;
 
   CUtensorMap tmA, tmB, tmO;
   int rc;
@@ -612,7 +556,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   {
     uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, b_mn_major ? 64u : (((cluster && !wide) || use_192) ? 64u : 128u)};
+    uint32_t box[2] = {64, (b_mn_major || use_192) ? 64u : 128u};  // rows per B box: must match the kernel's kBBox
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
   }
   if (p.tma_epi) {
@@ -624,14 +568,8 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   } else {
     tmO = tmA;  // unused
   }
-  // N == 384 (ViT-S proj / fc2, in-place residual): one 128 x 384 tile per CTA reads each A row block once
-  // (only worth it when the mainloop dominates: the single accumulator cannot overlap epilogue and MMAs)
-  if (p.tma_epi && use_192) return launch_gemm<192, 4, false, false>(tmA, tmB, tmO, p, stream);
-  if (p.tma_epi && use_384) return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
-  if (cluster && !(p.tma_epi == 0 && use_384)) {
-    if (wide) return launch_gemm<256, 3, false, false, true>(tmA, tmB, tmO, p, stream);
-    return launch_gemm<128, 5, false, false, true>(tmA, tmB, tmO, p, stream);
-  }
+  if (use_192) return launch_gemm<192, 4, false, false>(tmA, tmB, tmO, p, stream);
+  if (use_384) return launch_gemm<384, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (wide) return launch_gemm<256, 3, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && !b_mn_major) return launch_gemm<128, 5, false, false>(tmA, tmB, tmO, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);

@@ -305,7 +305,8 @@ linear_logits_kernel(const float* __restrict__ code, long long ld_code, int C, c
 
 struct LinearCEParams {
   const float* logits;   // [B*h*w][LP_LD]
-  const long long* label;  // [B][H][W]
+  const void* label;     // [B][H][W] int64 / int32 / uint8 (label_bytes = 8 / 4 / 1; uint8: 255 = ignore)
+  int label_bytes;
   int B, h, w, H, W, n;
   float* dlogits;        // [B*h*w][LP_LD] unnormalised gradient (atomics), or null (loss only)
   double* acc;           // [2]: loss sum, valid count (zeroed before the launch)
@@ -400,7 +401,12 @@ linear_ce_kernel(LinearCEParams p) {
   const int Y = Y0 + py, X = X0 + px;
   const bool inb = (Y < p.H) && (X < p.W);
   long long lab = -1;
-  if (inb) lab = p.label[(1ll * b * p.H + Y) * p.W + X];
+  if (inb) {
+    const long long li = (1ll * b * p.H + Y) * p.W + X;
+    if (p.label_bytes == 8) lab = reinterpret_cast<const long long*>(p.label)[li];
+    else if (p.label_bytes == 4) lab = reinterpret_cast<const int*>(p.label)[li];
+    else lab = reinterpret_cast<const unsigned char*>(p.label)[li];  // values >= n (e.g. 255) are ignored below
+  }
   const bool valid = inb && lab >= 0 && lab < n;
   float lsum = 0.f, cnt = 0.f;
   {
@@ -614,19 +620,21 @@ extern "C" int stego_cluster_lookup_bwd(const float* x, long long stride_b, long
 }
 
 // Linear probe + bilinear upsample + masked cross entropy, forward and (optionally) backward in one call.
-//   code [B*h*w][ld_code] fp32 tokens-major (detached), W [n][C], bias [n], label [B][H][W] int64
+//   code [B*h*w][ld_code] fp32 tokens-major (detached), W [n][C], bias [n], label [B][H][W] int64 / int32 / uint8
+//   (label_bytes = 8 / 4 / 1; a label outside [0, n) is ignored: -1 for the signed types, 255 for uint8)
 //   loss_out[0] = CE mean over valid pixels, loss_out[1] = number of valid pixels
 //   logits_scratch / dlogits_scratch: [B*h*w][32] floats (dlogits zeroed by the caller; null = forward only)
 //   dW / db: accumulated (+=) with grad_loss * d(loss)/d(.)
 extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C, const float* W, const float* bias,
-                                     int n_classes, const long long* label, int B, int h, int w, int H, int Wimg,
-                                     float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
+                                     int n_classes, const void* label, int label_bytes, int B, int h, int w, int H,
+                                     int Wimg, float* logits_scratch, float* dlogits_scratch, float* partials_scratch,
                                      float* loss_out, float grad_loss, float* dW, float* db, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(code && W && bias && label && logits_scratch && partials_scratch && loss_out,
                   "stego_linear_probe_ce: null pointer");
   STEGO_CHECK_ARG(C > 0 && C <= PR_MAX_DIM && n_classes > 0 && n_classes <= LP_LD,
                   "stego_linear_probe_ce: C=%d n=%d unsupported", C, n_classes);
+  STEGO_CHECK_ARG(label_bytes == 8 || label_bytes == 4 || label_bytes == 1, "stego_linear_probe_ce: label_bytes=%d (8, 4 or 1)", label_bytes);
   STEGO_CHECK_ARG(!dlogits_scratch || (dW && db), "stego_linear_probe_ce: backward needs dW and db");
   const long long rows = 1ll * B * h * w;
   {
@@ -637,7 +645,7 @@ extern "C" int stego_linear_probe_ce(const float* code, long long ld_code, int C
   }
   STEGO_CHECK_LAUNCH("linear_logits_kernel");
   LinearCEParams p;
-  p.logits = logits_scratch; p.label = label; p.B = B; p.h = h; p.w = w; p.H = H; p.W = Wimg; p.n = n_classes;
+  p.logits = logits_scratch; p.label = label; p.label_bytes = label_bytes; p.B = B; p.h = h; p.w = w; p.H = H; p.W = Wimg; p.n = n_classes;
   p.dlogits = dlogits_scratch;
   STEGO_CHECK_ARG((reinterpret_cast<uintptr_t>(partials_scratch) & 7u) == 0, "stego_linear_probe_ce: scratch not 8-byte aligned");
   p.acc = reinterpret_cast<double*>(partials_scratch);

@@ -13,8 +13,8 @@ namespace stego {
 // patchify: one thread per (patch, channel, ky): reads P contiguous pixels, writes P bf16.
 // column order c*P*P + ky*P + kx == flattening of the conv weight [E][3][P][P].
 // ---------------------------------------------------------------------------------------------
-template <int P>
-__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W) {
+template <int P, typename T>
+__global__ void patchify_kernel(const T* __restrict__ img, bf16* __restrict__ out, int B, int H, int W) {
   const int fh = H / P, fw = W / P;
   const long long total = 1ll * B * fh * fw * 3 * P;
   const long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,19 +25,24 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   const int px = patch % fw;
   const int py = (patch / fw) % fh;
   const int b = patch / (1ll * fw * fh);
-  const float* src = img + ((1ll * b * 3 + c) * H + (py * P + ky)) * W + px * P;
+  const T* src = img + ((1ll * b * 3 + c) * H + (py * P + ky)) * W + px * P;
   bf16* dst = out + patch * (3 * P * P) + c * P * P + ky * P;
   static_assert(P == 8 || P == 16, "patch size");
 #pragma unroll
   for (int v = 0; v < P / 8; ++v) {
-    const float4 a = *reinterpret_cast<const float4*>(src + v * 8);
-    const float4 b4 = *reinterpret_cast<const float4*>(src + v * 8 + 4);
-    uint4 w;
-    w.x = pack_bf16x2(a.x, a.y);
-    w.y = pack_bf16x2(a.z, a.w);
-    w.z = pack_bf16x2(b4.x, b4.y);
-    w.w = pack_bf16x2(b4.z, b4.w);
-    *reinterpret_cast<uint4*>(dst + v * 8) = w;
+    if constexpr (sizeof(T) == 2) {
+      // bf16 image (already the precision the GEMM operand has): a straight 16-byte copy
+      *reinterpret_cast<uint4*>(dst + v * 8) = *reinterpret_cast<const uint4*>(src + v * 8);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(src + v * 8);
+      const float4 b4 = *reinterpret_cast<const float4*>(src + v * 8 + 4);
+      uint4 w;
+      w.x = pack_bf16x2(a.x, a.y);
+      w.y = pack_bf16x2(a.z, a.w);
+      w.z = pack_bf16x2(b4.x, b4.y);
+      w.w = pack_bf16x2(b4.z, b4.w);
+      *reinterpret_cast<uint4*>(dst + v * 8) = w;
+    }
   }
 }
 
@@ -102,21 +107,38 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 
 using namespace stego;
 
-extern "C" int stego_vit_patchify(const float* img, void* out_bf16, int B, int H, int W, int patch, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int launch_patchify(const void* img, int img_is_bf16, void* out_bf16, int B, int H, int W, int patch,
+                           cudaStream_t stream) {
   STEGO_CHECK_ARG(img && out_bf16, "stego_vit_patchify: null pointer");
   STEGO_CHECK_ARG(patch == 8 || patch == 16, "stego_vit_patchify: patch size %d unsupported (8 or 16)", patch);
-  STEGO_CHECK_ARG(B > 0 && H % patch == 0 && W % patch == 0 && W % 4 == 0, "stego_vit_patchify: bad image %dx%dx%d", B, H, W);
+  STEGO_CHECK_ARG(B > 0 && H % patch == 0 && W % patch == 0 && W % 8 == 0, "stego_vit_patchify: bad image %dx%dx%d", B, H, W);
   STEGO_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15u) == 0, "stego_vit_patchify: image not 16-byte aligned");
   const long long total = 1ll * B * (H / patch) * (W / patch) * 3 * patch;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
-  if (patch == 8)
-    patchify_kernel<8><<<blocks, threads, 0, stream>>>(img, reinterpret_cast<bf16*>(out_bf16), B, H, W);
-  else
-    patchify_kernel<16><<<blocks, threads, 0, stream>>>(img, reinterpret_cast<bf16*>(out_bf16), B, H, W);
+  bf16* out = reinterpret_cast<bf16*>(out_bf16);
+  if (img_is_bf16) {
+    const bf16* im = reinterpret_cast<const bf16*>(img);
+    if (patch == 8) patchify_kernel<8, bf16><<<blocks, threads, 0, stream>>>(im, out, B, H, W);
+    else patchify_kernel<16, bf16><<<blocks, threads, 0, stream>>>(im, out, B, H, W);
+  } else {
+    const float* im = reinterpret_cast<const float*>(img);
+    if (patch == 8) patchify_kernel<8, float><<<blocks, threads, 0, stream>>>(im, out, B, H, W);
+    else patchify_kernel<16, float><<<blocks, threads, 0, stream>>>(im, out, B, H, W);
+  }
   STEGO_CHECK_LAUNCH("patchify_kernel");
   return STEGO_OK;
+}
+
+extern "C" int stego_vit_patchify(const float* img, void* out_bf16, int B, int H, int W, int patch, void* stream_) {
+  return launch_patchify(img, 0, out_bf16, B, H, W, patch, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// Same im2col for an image batch that is already bf16 (the GEMM operand precision): results are bit-identical to
+// feeding the fp32 image whenever the fp32 image holds bf16-representable values, and the H2D copy is half the size.
+extern "C" int stego_vit_patchify_bf16(const void* img_bf16, void* out_bf16, int B, int H, int W, int patch,
+                                       void* stream_) {
+  return launch_patchify(img_bf16, 1, out_bf16, B, H, W, patch, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int stego_vit_cls_rows(float* x, const float* cls_token, const float* pos_embed, int B, int ntok, int E,

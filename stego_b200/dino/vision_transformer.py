@@ -187,7 +187,8 @@ class VisionTransformer(nn.Module):
         if not img.is_cuda:
             raise RuntimeError("stego_b200: the DINO ViT forward only exists as sm_100a kernels (no CPU fallback)")
         w = self._prepared()
-        img = img.float().contiguous()
+        # bf16 images are taken as they are (patchify rounds fp32 images to bf16 anyway: same operand bits)
+        img = (img if img.dtype == torch.bfloat16 else img.float()).contiguous()
         B, _, H, W = img.shape
         p = self.patch_embed.patch_size
         E, heads = self.embed_dim, self.num_heads
@@ -204,26 +205,15 @@ class VisionTransformer(nn.Module):
         ao = torch.empty(B * N, E, dtype=torch.bfloat16, device=dev)
         hid = torch.empty(B * N, w["blocks"][0]["fc1_w"].shape[0], dtype=torch.bfloat16, device=dev)
         Hd = hid.shape[1]
-        # E == 384: the LayerNorm that follows each residual GEMM is computed in that GEMM's epilogue (one CTA holds
-        # a whole token row in TMEM), so the fp32 residual stream is not re-read by a separate LayerNorm kernel.
-        fused = ops.fused_ln_supported(E)
         blocks = w["blocks"]
-        for i, bw in enumerate(blocks):
-            if i == 0 or not fused:
-                ops.layernorm(x, bw["n1w"], bw["n1b"], y, eps=bw["eps1"])
+        for bw in blocks:
+            ops.layernorm(x, bw["n1w"], bw["n1b"], y, eps=bw["eps1"])
             ops.gemm(y, bw["qkv_w"], qkv, M=B * N, N=3 * E, K=E, bias=bw["qkv_b"])
             ops.attention(qkv, ao, B, N, E, heads)
-            if fused:
-                ops.gemm_residual_ln(ao, bw["proj_w"], x, bw["proj_b"], bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
-            else:
-                ops.gemm(ao, bw["proj_w"], x, M=B * N, N=E, K=E, bias=bw["proj_b"], residual=x)
-                ops.layernorm(x, bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
+            ops.gemm(ao, bw["proj_w"], x, M=B * N, N=E, K=E, bias=bw["proj_b"], residual=x)
+            ops.layernorm(x, bw["n2w"], bw["n2b"], y, eps=bw["eps2"])
             ops.gemm(y, bw["fc1_w"], hid, M=B * N, N=Hd, K=E, bias=bw["fc1_b"], act=ops.ACT_GELU)
-            if fused and i + 1 < len(blocks):
-                nx = blocks[i + 1]
-                ops.gemm_residual_ln(hid, bw["fc2_w"], x, bw["fc2_b"], nx["n1w"], nx["n1b"], y, eps=nx["eps1"])
-            else:
-                ops.gemm(hid, bw["fc2_w"], x, M=B * N, N=E, K=Hd, bias=bw["fc2_b"], residual=x)
+            ops.gemm(hid, bw["fc2_w"], x, M=B * N, N=E, K=Hd, bias=bw["fc2_b"], residual=x)
         return x, (qkv if want_qkv else None)
 
     @torch.no_grad()
@@ -248,12 +238,13 @@ class VisionTransformer(nn.Module):
         graphs = self._cache.setdefault("graphs", {})
         parts = list(img) if isinstance(img, (list, tuple)) else [img]
         shape = (sum(p.shape[0] for p in parts),) + tuple(parts[0].shape[1:])
-        key = (shape, parts[0].device.index)
+        dt = torch.bfloat16 if all(p.dtype == torch.bfloat16 for p in parts) else torch.float32
+        key = (shape, parts[0].device.index, dt)
         if key not in graphs:
-            img = torch.cat(parts, 0) if len(parts) > 1 else parts[0]
+            img = torch.cat([p.to(dt) for p in parts], 0) if len(parts) > 1 else parts[0].to(dt)
             self._patch_features_eager(img)  # warm-up: kernel attributes, pos-embed cache, allocator
             torch.cuda.synchronize()
-            static_in = img.detach().float().contiguous().clone()
+            static_in = img.detach().contiguous().clone()
             g = torch.cuda.CUDAGraph()
             n0 = _lib.load().stego_launch_count()
             with torch.cuda.graph(g):

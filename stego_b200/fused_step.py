@@ -25,6 +25,10 @@ import torch
 from . import _lib, corr, ops
 
 
+# label dtypes the linear-probe CE kernel reads directly (int64 is the reference's; uint8 uses 255 = ignore)
+_LABEL_BYTES = {torch.int64: 8, torch.int32: 4, torch.uint8: 1}
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -41,6 +45,7 @@ class FusedStep:
         self.key = None
         self.side = None
         self.step_idx = 0
+        self.update_done = None
 
     # ------------------------------------------------------------------------------------------
     def supported(self, batch) -> bool:
@@ -51,10 +56,10 @@ class FusedStep:
                 and cfg.rec_weight == 0 and cfg.aug_alignment_weight == 0 and cfg.crf_weight == 0
                 and cfg.neg_samples >= 1 and cfg.dino_feat_type == "feat"
                 and seg.linear_probe.weight.shape[0] <= 32 and seg.net.dim <= 96
-                and batch["label"].dtype == torch.long)
+                and batch["label"].dtype in _LABEL_BYTES)
 
     # ------------------------------------------------------------------------------------------
-    def _alloc(self, B, H, W, LH, LW, dev):
+    def _alloc(self, B, H, W, LH, LW, dev, label_dtype):
         seg, cfg, net = self.seg, self.seg.cfg, self.seg.net
         ws = _Workspace()
         E, D = net.n_feats, net.dim
@@ -101,13 +106,14 @@ class FusedStep:
         n_clu = seg.cluster_probe.clusters.shape[0]
         ws.n_lin, ws.n_clu = n_lin, n_clu
         ws.logits = torch.empty(B * hw, 32, dtype=f32, device=dev)
-        ws.ce_partials = torch.empty(16 * 160 * 2, dtype=f32, device=dev)
+        ws.ce_partials = torch.empty(16 * ws.num_sms * 2, dtype=f32, device=dev)
         ws.lin_loss = torch.empty(2, dtype=f32, device=dev)
         ws.clu_loss = torch.empty(2, dtype=f32, device=dev)
-        ws.clu_scratch = torch.empty(16 * 160, dtype=f32, device=dev)
+        ws.clu_scratch = torch.empty(16 * ws.num_sms, dtype=f32, device=dev)
         ws.one = torch.ones(1, dtype=f32, device=dev)
         ws.out4 = torch.empty(4, dtype=f32, device=dev)
-        ws.label = torch.empty(B, LH, LW, dtype=torch.long, device=dev)  # static copy: the tail graph bakes pointers
+        ws.label = torch.empty(B, LH, LW, dtype=label_dtype, device=dev)  # static copy: the tail graph bakes pointers
+        ws.label_bytes = _LABEL_BYTES[label_dtype]
         ws.graph = None
         ws.eager_steps = 0
         # everything the kernels accumulate into: ONE buffer, ONE memset per step
@@ -193,7 +199,8 @@ class FusedStep:
         lab = ws.label
         LH, LW = ws.label_shape
         _lib.check(lib.stego_linear_probe_ce(
-            _lib.ptr(ws.code), P, D, _lib.ptr(lp.weight), _lib.ptr(lp.bias), ws.n_lin, _lib.ptr(lab), B, fh, fw, LH, LW,
+            _lib.ptr(ws.code), P, D, _lib.ptr(lp.weight), _lib.ptr(lp.bias), ws.n_lin, _lib.ptr(lab), ws.label_bytes, B, fh, fw,
+            LH, LW,
             _lib.ptr(ws.logits), _lib.ptr(ws.dlogits), _lib.ptr(ws.ce_partials), _lib.ptr(ws.lin_loss), 1.0,
             _lib.ptr(lp.weight.grad), _lib.ptr(lp.bias.grad), st), "stego_linear_probe_ce")
         cl = seg.cluster_probe.clusters
@@ -251,26 +258,31 @@ class FusedStep:
         LH, LW = label.shape[-2], label.shape[-1]
         if seg._flat is None:
             seg.configure_optimizers()
+        seg._flat.ensure_bound()  # parameters / .grad still are the views into the flat buffers the kernels write
         net_optim, linear_probe_optim, cluster_probe_optim = seg.optimizers()
-        key = (B, H, W, LH, LW, dev.index, id(seg._flat))  # a new flat parameter buffer invalidates the captured graph
+        # a new flat parameter buffer (or another label dtype) invalidates the captured graph
+        key = (B, H, W, LH, LW, dev.index, id(seg._flat), label.dtype)
         if self.key != key:
-            self.ws = self._alloc(B, H, W, LH, LW, dev)
+            self.flush()
+            self.ws = self._alloc(B, H, W, LH, LW, dev, label.dtype)
             self.key = key
             self.side = torch.cuda.Stream(device=dev)
         ws = self.ws
         B, E, D, P, fh, fw, hw, M, nonlinear = ws.dims
-        spec = seg._spec
         main = torch.cuda.current_stream()
         seg._mark("start")
 
-        # ---- prologue on the side stream, overlapped with the ViT
-        self.side.wait_stream(main)  # the previous step (consumers of the workspace, Adam) is complete
+        # ---- side stream: [gradient all-reduce + Adam of the PREVIOUS step, enqueued at the end of that step] ->
+        #      prologue of this step.  The frozen ViT on the main stream depends on neither, so the whole update
+        #      (the one collective of the data-parallel step included) is hidden under the next step's backbone.
+        self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self._prologue(ws)
             ready = torch.cuda.Event()
             ready.record(self.side)
 
         use_graph = bool(getattr(cfg, "cuda_graph", True)) and seg.profile_marks is None
+        overlap = bool(getattr(cfg, "overlap_update", True)) and seg.profile_marks is None
         with torch.no_grad():
             tok_all = net.backbone_tokens([img, img_pos], use_graph=getattr(cfg, "cuda_graph", True))  # [2B,hw,E] bf16
             ws.label.copy_(label.reshape(B, LH, LW))
@@ -294,15 +306,27 @@ class FusedStep:
                 self._tail(ws, tok_all)
                 ws.eager_steps += 1
             seg._mark("backward")
-
-            from .segmenter import allreduce_gradients
-            allreduce_gradients(seg._flat)
-            net_optim.step()
-            cluster_probe_optim.step()
-            linear_probe_optim.step()
-            seg._mark("allreduce_adam")
             out4 = ws.out4
             loss = out4[0].clone()  # the workspace is overwritten by the next step; the returned loss is not
+
+            # ---- update: all-reduce (N > 1) + three fused Adam launches (+ the probe reset of
+            #      train_segmentation.py:232-237) on the side stream, behind the tail
+            tail_done = torch.cuda.Event()
+            tail_done.record(main)
+            self.side.wait_event(tail_done)
+            with torch.cuda.stream(self.side):
+                from .segmenter import allreduce_gradients
+                allreduce_gradients(seg._flat)
+                net_optim.step()
+                cluster_probe_optim.step()
+                linear_probe_optim.step()
+                if cfg.reset_probe_steps is not None and seg.global_step == cfg.reset_probe_steps:
+                    seg.reset_probes()
+                self.update_done = torch.cuda.Event()
+                self.update_done.record(self.side)
+            if not overlap:
+                main.wait_event(self.update_done)
+            seg._mark("allreduce_adam")
 
         # logging (views of the workspace: valid until the next step overwrites them)
         seg.log('loss/pos_intra', ws.stats[0, 0])
@@ -317,3 +341,11 @@ class FusedStep:
         self.step_idx += 1
         seg.global_step += 1
         return loss
+
+    def flush(self):
+        """Make the current stream wait for the parameter update of the last step (it runs on the side stream so that
+        the next step's frozen backbone can overlap it).  Anything that reads parameters, gradients or optimiser
+        state outside training_step — validation forward, checkpointing, tests — goes through here
+        (LitUnsupervisedSegmenter.flush / forward / state_dict call it)."""
+        if self.update_done is not None:
+            torch.cuda.current_stream().wait_event(self.update_done)

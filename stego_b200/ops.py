@@ -38,39 +38,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     return out
 
 
-def gemm_residual_ln(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Tensor],
-                     gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    """x += a.w^T + bias (fp32, in place);  y = LayerNorm(x)*gamma+beta (bf16) in one kernel
-    (stego_gemm_residual_ln_bf16; N = w.shape[0] must be 384)."""
-    _lib.require_cuda(a, w, x, bias, gamma, beta, y)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dtype == torch.float32
-    assert y.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1 and x.stride(1) == 1 and y.stride(1) == 1
-    M, K = a.shape
-    N = w.shape[0]
-    assert w.shape[1] == K and x.shape == (M, N) and y.shape == (M, N)
-    rc = _lib.load().stego_gemm_residual_ln_bf16(
-        _lib.ptr(a), a.stride(0), _lib.ptr(w), w.stride(0), M, N, K, _lib.ptr(x), x.stride(0), _lib.ptr(bias),
-        _lib.ptr(gamma), _lib.ptr(beta), float(eps), _lib.ptr(y), y.stride(0), _lib.stream())
-    _lib.check(rc, "stego_gemm_residual_ln_bf16")
-    return y
-
-
-def fused_ln_supported(E: int) -> bool:
-    """Whether the ViT uses the fused residual-GEMM + LayerNorm kernel (one CTA keeps a whole 384-wide row in TMEM).
-    Opt-in (STEGO_FUSED_LN=1): with a single accumulator the epilogue cannot overlap the next tile's MMAs, and on
-    B200 it measured 5% slower end to end than the separate GEMM + LayerNorm kernels (profiles/README_r1.md)."""
-    import os
-    return E == 384 and os.environ.get("STEGO_FUSED_LN", "0") == "1"
-
-
 def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
-    """PatchEmbed im2col rows [B*hw, 3*p*p] bf16 (stego_vit_patchify)."""
+    """PatchEmbed im2col rows [B*hw, 3*p*p] bf16 (stego_vit_patchify / stego_vit_patchify_bf16)."""
     _lib.require_cuda(img)
-    assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
+    assert img.dtype in (torch.float32, torch.bfloat16) and img.is_contiguous() and img.shape[1] == 3
     B, _, H, W = img.shape
     out = torch.empty(B * (H // patch) * (W // patch), 3 * patch * patch, dtype=torch.bfloat16, device=img.device)
-    _lib.check(_lib.load().stego_vit_patchify(_lib.ptr(img), _lib.ptr(out), B, H, W, patch, _lib.stream()),
-               "stego_vit_patchify")
+    lib = _lib.load()
+    fn = lib.stego_vit_patchify if img.dtype == torch.float32 else lib.stego_vit_patchify_bf16
+    _lib.check(fn(_lib.ptr(img), _lib.ptr(out), B, H, W, patch, _lib.stream()), "stego_vit_patchify")
     return out
 
 

@@ -56,6 +56,47 @@ class FusedAdam:
         g = self.group
         self.owner.grad[g.start:g.start + g.numel].zero_()
 
+    def reset_state(self):
+        """Fresh optimiser state for this group (what constructing a new torch.optim.Adam does)."""
+        g = self.group
+        self.owner.exp_avg[g.start:g.start + g.numel].zero_()
+        self.owner.exp_avg_sq[g.start:g.start + g.numel].zero_()
+        self.steps = 0
+
+    def state_dict(self):
+        """torch.optim.Adam layout (per-parameter `step`, `exp_avg`, `exp_avg_sq`), so a checkpoint written here resumes
+        under torch.optim.Adam and vice versa."""
+        g, o = self.group, self.owner
+        state, off = {}, g.start
+        for i, p in enumerate(g.params):
+            n = p.numel()
+            if self.steps > 0:
+                state[i] = dict(step=torch.tensor(float(self.steps)),
+                                exp_avg=o.exp_avg[off:off + n].view(p.shape).clone(),
+                                exp_avg_sq=o.exp_avg_sq[off:off + n].view(p.shape).clone())
+            off += n
+        pg = self.param_groups[0]
+        return dict(state=state, param_groups=[dict(lr=pg["lr"], betas=pg["betas"], eps=pg["eps"], weight_decay=0,
+                                                    amsgrad=False, params=list(range(len(g.params))))])
+
+    def load_state_dict(self, sd):
+        g, o = self.group, self.owner
+        pg = sd["param_groups"][0]
+        self.param_groups[0].update(lr=pg["lr"], betas=tuple(pg["betas"]), eps=pg["eps"])
+        off, steps = g.start, 0
+        for i, p in enumerate(g.params):
+            n = p.numel()
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                o.exp_avg[off:off + n].zero_()
+                o.exp_avg_sq[off:off + n].zero_()
+            else:
+                o.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                o.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps = max(steps, int(float(st["step"])))
+            off += n
+        self.steps = steps
+
     def step(self):
         g, o = self.group, self.owner
         self.steps += 1
@@ -91,6 +132,21 @@ class FlatParams:
                 off += n
             self.groups.append(fg)
         self.optimizers = [FusedAdam(self, g) for g in self.groups]
+
+    def ensure_bound(self):
+        """The fused kernels write through raw pointers into the flat buffers: every parameter (and its .grad) must
+        still be the view made at construction.  `.grad = None` (zero_grad(set_to_none=True)) is repaired here; a
+        parameter whose storage moved (model.to() / .cuda() after configure_optimizers) cannot be, and raises."""
+        for g in self.groups:
+            off = g.start
+            for p in g.params:
+                n = p.numel()
+                if p.data_ptr() != self.param.data_ptr() + 4 * off:
+                    raise RuntimeError("stego_b200: a trainable parameter no longer lives in the flat parameter buffer "
+                                       "(model moved after configure_optimizers()?); call configure_optimizers() again")
+                if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                    p.grad = self.grad[off:off + n].view(p.shape)
+                off += n
 
     def rebind(self):
         """Autograd may replace .grad objects; point them back at the flat buffer (values are accumulated
@@ -137,16 +193,22 @@ class _LinearProbeCEFn(torch.autograd.Function):
         ld = x.stride(3)
         rows = B * h * w
         H, W = label.shape[-2], label.shape[-1]
-        lab = label.reshape(B, H, W).to(torch.long).contiguous()
+        lab = label.reshape(B, H, W)
+        if lab.dtype not in (torch.int64, torch.int32, torch.uint8):
+            lab = lab.to(torch.long)
+        lab = lab.contiguous()
+        label_bytes = {torch.int64: 8, torch.int32: 4, torch.uint8: 1}[lab.dtype]
         logits = torch.empty(rows, 32, dtype=torch.float32, device=dev)
         dlogits = torch.zeros(rows, 32, dtype=torch.float32, device=dev)
-        partials = torch.empty(16 * 160 * 2, dtype=torch.float32, device=dev)
+        partials = torch.empty(16 * torch.cuda.get_device_properties(dev).multi_processor_count * 2,
+                               dtype=torch.float32, device=dev)
         loss = torch.empty(2, dtype=torch.float32, device=dev)
         dW = torch.zeros(n, C, dtype=torch.float32, device=dev)
         db = torch.zeros(n, dtype=torch.float32, device=dev)
         wf = weight.detach().float().reshape(n, C).contiguous()
         bf = bias.detach().float().contiguous()
-        rc = _lib.load().stego_linear_probe_ce(_lib.ptr(x), ld, C, _lib.ptr(wf), _lib.ptr(bf), n, _lib.ptr(lab), B, h, w,
+        rc = _lib.load().stego_linear_probe_ce(_lib.ptr(x), ld, C, _lib.ptr(wf), _lib.ptr(bf), n, _lib.ptr(lab), label_bytes, B,
+                                               h, w,
                                                H, W, _lib.ptr(logits), _lib.ptr(dlogits), _lib.ptr(partials),
                                                _lib.ptr(loss), 1.0, _lib.ptr(dW), _lib.ptr(db), _lib.stream())
         _lib.check(rc, "stego_linear_probe_ce")
@@ -200,7 +262,30 @@ class LitUnsupervisedSegmenter(nn.Module):
 
     # ---- Lightning-shaped surface ----------------------------------------------------------------
     def forward(self, x):
+        self.flush()
         return self.net(x)[1]
+
+    def flush(self):
+        """The hand-scheduled step leaves its parameter update (all-reduce + Adam) on a side stream so that the next
+        step's frozen backbone overlaps it; this makes the CURRENT stream wait for it.  Call it before reading
+        parameters / gradients / optimiser state outside training_step (forward and state_dict do)."""
+        if self._fused is not None:
+            self._fused.flush()
+
+    def state_dict(self, *args, **kwargs):
+        self.flush()
+        return super().state_dict(*args, **kwargs)
+
+    def reset_probes(self):
+        """train_segmentation.py:232-237: re-initialise both probes and give them fresh Adam state (runs on the
+        current stream; the parameters stay views of the flat buffer, so captured graphs remain valid)."""
+        print("RESETTING PROBES")
+        with torch.no_grad():
+            self.linear_probe.reset_parameters()
+            self.cluster_probe.reset_parameters()
+        _, linear_probe_optim, cluster_probe_optim = self.optimizers()
+        linear_probe_optim.reset_state()
+        cluster_probe_optim.reset_state()
 
     def log(self, name, value, **_kwargs):
         self.logged[name] = value.detach() if torch.is_tensor(value) else value
@@ -212,7 +297,12 @@ class LitUnsupervisedSegmenter(nn.Module):
         if self.cfg.rec_weight > 0:
             main.extend(self.decoder.parameters())
         groups = [main, list(self.linear_probe.parameters()), list(self.cluster_probe.parameters())]
+        self.flush()
         self._flat = FlatParams(groups, [self.cfg.lr, 5e-3, 5e-3])
+        import torch.distributed as dist
+        if self._flat.param.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # Lightning-DDP broadcasts module state from rank 0 when it wraps the model (train_segmentation.py:476)
+            dist.broadcast(self._flat.param, src=0)
         return tuple(self._flat.optimizers)
 
     def optimizers(self):
@@ -241,6 +331,7 @@ class LitUnsupervisedSegmenter(nn.Module):
 
     def _training_step_autograd(self, batch, batch_idx):
         cfg = self.cfg
+        self.flush()
         net_optim, linear_probe_optim, cluster_probe_optim = self.optimizers()
         net_optim.zero_grad()
         linear_probe_optim.zero_grad()
@@ -343,6 +434,6 @@ class LitUnsupervisedSegmenter(nn.Module):
         self._mark("allreduce_adam")
 
         if cfg.reset_probe_steps is not None and self.global_step == cfg.reset_probe_steps:
-            raise RuntimeError("stego_b200: reset_probe_steps is not supported on the flat-buffer optimiser yet")
+            self.reset_probes()
         self.global_step += 1
         return loss
