@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — STEGO correspondence-distillation training step on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4] [--impl ours|reference|torch-eager]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 A "step" is one full training step of the hot path on one synthetic batch per GPU: 2x frozen DINO ViT
@@ -17,7 +17,12 @@ One JSON line on rank 0:
   corr_roofline  the named correlation+loss kernel against BOTH the bf16 tensor peak and the HBM peak
   cpu_baseline   the oracle port (CPU restatement of the reference, oracle/stego_oracle.py) on the host cores,
                  bounded sample
-`--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
+  sustained      the same device-resident loop run for >= 5 s with its own clock record
+`--impl reference` times the reference's CPU path alone (rank 0 only; the REAL reference classes from baseline/_ref
+through oracle/lightning_harness.py when that copy is present — `cpu_baseline.kind` "reference" — else the oracle port)
+and prints the same line shape.  `--impl torch-eager` runs the unmodified reference modules.py / vision_transformer.py /
+training_step text in PyTorch eager ON THE GPU (fp32 defaults and bf16 autocast) plus the library kernels (cuBLAS
+GEMMs, SDPA) at the step's shapes: the "reference PyTorch path on B200" comparator.
 """
 from __future__ import annotations
 
@@ -195,6 +200,142 @@ def time_cpu(model_type, res, batch, steps, warmup, budget_s=150.0):
         step()
     dt = (time.perf_counter() - t0) / steps
     return batch / dt, dt, best_c, steps
+
+
+def reference_step_fn(model_type, res, batch, device, autocast=False):
+    """One training step of the REAL reference (src/train_segmentation.py:112-245 over src/modules.py and
+    src/dino/vision_transformer.py, all unmodified, from baseline/_ref) behind the stub-Lightning harness.  Returns
+    step() or None when the reference copy is not present."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lightning_harness as H
+    if not H.available():
+        return None
+    import tempfile
+    from stego_b200.config import make_cfg
+    ts = H.load_reference_segmenter("reference")
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "dino.pth")
+        H.write_random_dino_checkpoint(ck, model_type, seed=0, perturb=False)
+        cfg = make_cfg(model_type=model_type, res=res, batch_size=batch, pretrained_weights=ck)
+        torch.manual_seed(0)
+        m = ts.LitUnsupervisedSegmenter(N_CLASSES, cfg)
+    m = m.to(device)
+    m.train()
+    b = H.make_batch(batch, res, device, seed=2)
+    it = [0]
+
+    def step():
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = m.training_step(b, it[0])
+        else:
+            loss = m.training_step(b, it[0])
+        m.global_step += 1
+        it[0] += 1
+        return loss
+
+    return step
+
+
+def time_reference_cpu(model_type, res, batch, steps, warmup, budget_s=150.0):
+    """The reference itself on the host cores (all threads torch picks; probed like time_cpu).  None if unavailable."""
+    step = reference_step_fn(model_type, res, batch, "cpu")
+    if step is None:
+        return None
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (avail, 64, 32, 16) if c <= avail}) or [avail]
+    torch.set_num_threads(cands[0])
+    step()
+    best_t, best_c, t_spent = None, cands[0], 0.0
+    for c in cands:
+        if best_t is not None and t_spent > budget_s / 3:
+            break
+        torch.set_num_threads(c)
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        t_spent += dt
+        if best_t is None or dt < best_t:
+            best_t, best_c = dt, c
+        elif dt > 1.5 * best_t:
+            break
+    torch.set_num_threads(best_c)
+    for _ in range(max(0, min(warmup, 1))):
+        step()
+    steps = max(1, min(steps, int(max(budget_s - t_spent, 1.0) / max(best_t, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt, best_c, steps
+
+
+def run_torch_eager(args, cfgd, workload):
+    """The reference PyTorch path on the B200: unmodified reference modules in eager mode (what PyTorch 2.11 dispatches
+    — cuBLAS / cuDNN / ATen), fp32 (PyTorch defaults: TF32 off for matmul) and under bf16 autocast, plus the library
+    kernels at the step's GEMM / attention shapes.  One JSON line; `value` is the bf16-autocast images/s."""
+    import torch.nn.functional as F
+    model_type, res, B = cfgd["model_type"], cfgd["res"], cfgd["batch"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = {}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        try:
+            step = reference_step_fn(model_type, res, B, dev, autocast=ac)
+            if step is None:
+                print(json.dumps({"impl": "torch-eager", "unavailable": "baseline/_ref (reference copy) not present"}))
+                return
+            for _ in range(max(args.warmup, 3)):
+                step()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(args.steps):
+                step()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / args.steps
+            out[name] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms}
+        except torch.cuda.OutOfMemoryError as ex:
+            out[name] = {"error": "out of memory: " + str(ex)[:120]}
+        torch.cuda.empty_cache()
+    # library kernels at this config's shapes (2B images through the ViT)
+    E, heads, hw, N = vit_dims(model_type, res)
+    M = 2 * B * N
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    lib = {}
+
+    def mm(name, Nn, K):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(Nn, K, device=dev) * K ** -0.5).bfloat16()
+        bias = torch.randn(Nn, device=dev).bfloat16()
+        ms = time_kernel(lambda: F.linear(a, w, bias), flush=flush)
+        lib[name] = {"ms": ms, "tflops": 2.0 * M * Nn * K / ms / 1e9}
+
+    mm("cublas_qkv", 3 * E, E)
+    mm("cublas_proj", E, E)
+    mm("cublas_fc1", 4 * E, E)
+    mm("cublas_fc2", E, 4 * E)
+    q = torch.randn(2 * B, heads, N, 64, device=dev).bfloat16()
+    k, v = torch.randn_like(q), torch.randn_like(q)
+    ms = time_kernel(lambda: F.scaled_dot_product_attention(q, k, v), flush=flush)
+    lib["sdpa_bf16"] = {"ms": ms, "tflops": 2.0 * 2 * 2 * B * N * N * E / ms / 1e9}
+    xr = torch.randn(M, E, device=dev)
+    ln = torch.nn.LayerNorm(E, eps=1e-6).to(dev)
+    ms = time_kernel(lambda: ln(xr), flush=flush)
+    lib["aten_layernorm_fp32"] = {"ms": ms}
+    best = out.get("bf16_autocast", {}).get("images_per_s") or out.get("fp32", {}).get("images_per_s")
+    print(json.dumps({
+        "impl": "torch-eager", "metric": "train-step images/sec", "value": best, "unit": "images/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 autocast (value) / fp32", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": B, "parallelism": "dp1",
+                   "what": "unmodified reference modules.py + dino/vision_transformer.py + training_step text "
+                           "(baseline/_ref) in PyTorch eager on the B200"},
+        "modes": out, "library_kernels": lib}))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -431,7 +572,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
+    ap.add_argument("--sustain-seconds", type=float, default=5.0, help="length of the extra sustained-clock run (0 = skip)")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
@@ -448,20 +590,34 @@ def main():
     model_type, res, B = cfgd["model_type"], cfgd["res"], cfgd["batch"]
     workload = f"{args.config}: {cfgd['desc']}; synthetic N(0,1) images, random-init weights"
 
-    if args.impl == "reference":
-        # the reference's CPU implementation of the path (oracle port), rank 0 only, bounded sample per step
+    if args.impl == "torch-eager":
         if rank != 0:
             return
-        sample_b = 2
-        v, dt, cores, nst = time_cpu(model_type, res, sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
+        return run_torch_eager(args, cfgd, workload)
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, rank 0 only, bounded sample per step: the REAL reference
+        # (baseline/_ref through the stub-Lightning harness) when that copy travelled with the repo, else the oracle port
+        if rank != 0:
+            return
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # a CPU arm: the reference's unconditional .cuda() must not find a GPU
+        sample_b = {"c1": 8, "c2": 2, "c3": 1}.get(args.config, 2)
+        kind = "reference"
+        r = time_reference_cpu(model_type, res, sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
+        if r is None:
+            kind, sample_b = "port", 2
+            r = time_cpu(model_type, res, sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
+        v, dt, cores, nst = r
+        what = ("the reference's own LitUnsupervisedSegmenter.training_step (baseline/_ref, unmodified, stub Lightning base)"
+                if kind == "reference" else "the oracle port")
         print(json.dumps({
             "impl": "reference", "metric": "train-step images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": nst, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "global_batch": sample_b, "parallelism": "cpu"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
                              "sample": f"batch {sample_b} per step of the {args.config} workload (full step: 2x ViT fwd, "
-                                       "head, loss, probes, backward, Adam) with the oracle port on all host threads"},
+                                       f"head, loss, probes, backward, 3x Adam) with {what} on {cores} host threads"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -483,7 +639,16 @@ def main():
                 img_pos=torch.randn(B, 3, res, res, generator=gdata).pin_memory(),
                 label=torch.randint(-1, N_CLASSES, (B, res, res), generator=gdata).pin_memory())
     batch = {k: v.to(dev) for k, v in host.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    # the same batch as the public API also accepts it: bf16 images (patchify rounds the fp32 image to bf16 — the GEMM
+    # operand — anyway) and uint8 labels (classes 0..26, 255 = ignore instead of -1): 2.4x fewer bytes over PCIe.  The
+    # images here are rounded to bf16 on the host, so this path gives the same loss as the fp32/int64 one would on
+    # bf16-representable pixels.
+    lab8 = host["label"].clone()
+    lab8[lab8 < 0] = 255
+    host_compact = dict(img=host["img"].bfloat16().pin_memory(), img_pos=host["img_pos"].bfloat16().pin_memory(),
+                        label=lab8.to(torch.uint8).pin_memory())
+    h2d_of = lambda hb: sum(v.numel() * v.element_size() for v in hb.values())
+    h2d = h2d_of(host)
     loss_host = torch.zeros(1).pin_memory()
     loss_ring = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
 
@@ -494,33 +659,34 @@ def main():
 
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def stage_batch():
+    def stage_batch(hb):
         """H2D copy of one step's inputs from pinned host memory on a side stream (overlaps the previous step)."""
         with torch.cuda.stream(copy_stream):
-            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return b, ev
 
     host_ms = [0.0]
 
-    def run(nsteps, e2e):
+    def run(nsteps, e2e, hb=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         if e2e:
+            hb = hb if hb is not None else host
             # every step: inputs come from pinned host memory (H2D inside the timed region, prefetched one step
             # ahead on a copy stream like a pin_memory DataLoader) and the step's loss is read back to the host
             # (D2H, one step delayed so the host never stalls the launch queue).
             pending = []
-            nxt = stage_batch()
+            nxt = stage_batch(hb)
             for i in range(nsteps):
                 b, ev = nxt
                 torch.cuda.current_stream().wait_event(ev)
                 for t in b.values():
                     t.record_stream(torch.cuda.current_stream())
                 if i + 1 < nsteps:
-                    nxt = stage_batch()
+                    nxt = stage_batch(hb)
                 loss = model.training_step(b, i)
                 slot = loss_ring[i % 2]
                 slot.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -555,8 +721,22 @@ def main():
     host_enqueue_ms = host_ms[0]
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    run(min(args.warmup, 3), True)
-    ms_e2e = run(args.steps, True)
+    run(min(args.warmup, 3), True, host_compact)
+    ms_e2e = run(args.steps, True, host_compact)
+    run(min(args.warmup, 3), True, host)
+    ms_e2e_full = run(args.steps, True, host)
+    # sustained regime: the same device-resident loop for >= --sustain-seconds, with its own clock record (a 20-step
+    # timed region is ~0.1 s of burst clocks)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / (ms_dev / args.steps)) + 1)
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = run(n_sus, False)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "ms_per_step": ms_sus / n_sus,
+                     "value": B * world * n_sus / (ms_sus / 1e3), "unit": "images/s", "clocks": clocks2}
     phases = None
     if args.breakdown:
         model.profile_marks = []
@@ -577,6 +757,7 @@ def main():
     img_per_step = B * world
     value = img_per_step * args.steps / (ms_dev / 1e3)
     e2e_value = img_per_step * args.steps / (ms_e2e / 1e3)
+    e2e_full_value = img_per_step * args.steps / (ms_e2e_full / 1e3)
     fl_img = step_flops_per_image(model_type, res)
     line = {
         "metric": "train-step images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -585,8 +766,14 @@ def main():
         "config": {"workload": workload, "global_batch": img_per_step, "per_gpu_batch": B, "res": res,
                    "parallelism": f"dp{world}", "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; "
                                                       "no explicit flush between steps"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_of(host_compact), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps,
+                "inputs": "LitUnsupervisedSegmenter.training_step with pinned-host bf16 images + uint8 labels (255 = "
+                          "ignore) copied H2D every step, loss read back D2H every step"},
+        "e2e_fp32_int64_inputs": {"value": e2e_full_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_full / args.steps,
+                                  "inputs": "the reference DataLoader's dtypes: fp32 images + int64 labels"},
+        **({"sustained": sustained} if sustained else {}),
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks,
         "last_loss": loss_val,
         **({"phase_ms": {k: round(v, 4) for k, v in phases.items()}} if phases else {}),
@@ -603,13 +790,17 @@ def main():
                   key=lambda k: ks[k]["share_of_step"])
         d = ks[dom]
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+        traffic_src = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
         if os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+            # THIS build's kernels at these shapes (a profiler cannot run inside the timed region); see `traffic_source`
             tj = json.load(open(tpath))
             if tj.get("config") == args.config and not args.batch:
                 traffic = tj["bytes_per_launch"].get(dom)
+                traffic_src = tj.get("source")
         line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peaks["tf_burst"],
-                            "unit": "TFLOP/s", "frac": d["tflops"] / peaks["tf_burst"], "traffic": traffic,
+                            "unit": "TFLOP/s", "frac": d["tflops"] / peaks["tf_burst"], "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes_per_launch": d["bytes"],
                             "algorithmic_flops_per_launch": d["flops"], "ms_per_launch": d["ms"],
                             "share_of_step": d["share_of_step"], "peak_source": peaks["source"] + ", burst"}
