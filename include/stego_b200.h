@@ -70,6 +70,10 @@ STEGO_API int stego_vit_cls_rows(float* x, const float* cls_token, const float* 
  * (src/modules.py:97). E in {128, 384, 768}. */
 STEGO_API int stego_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows,
                                    int E, float eps, int drop_cls_ntok, void* stream);
+/* Final norm fused with the global average pool of src/precompute_knns.py:19 (`model(img).mean([2, 3])`): x fp32
+ * [B][ntok][E] residual stream -> out fp32 [B][E] (+=; zero it first) = mean over the ntok-1 patch tokens of LayerNorm(x). */
+STEGO_API int stego_layernorm_gap(const float* x, const float* gamma, const float* beta, float* out, int B, int ntok,
+                                  int E, float eps, void* stream);
 /* Attention.forward (:78-90) without the projections: softmax(q k^T / sqrt(64)) v, fused (flash-style) on
  * tcgen05; qkv [B][N][3E] bf16 packed q|k|v with heads contiguous inside each third, out [B][N][E] bf16. */
 STEGO_API int stego_attention_fwd(const void* qkv, void* out, int B, int N, int E, int heads, void* stream);
@@ -182,12 +186,18 @@ STEGO_API int stego_linear_probe_ce(const float* code, long long ld_code, int C,
  *   code: tokens-major low-res code [B*h*w][ld_code] fp32; lin_weight [n_lin][C], lin_bias [n_lin], clusters [n_clu][C];
  *   lr_scratch: [B*h*w][72] floats.  Outputs (each may be null): log-probabilities [B][n][H][W] fp32 and
  *   per-pixel argmax maps [B][H][W] uint8.  C <= 96, n_lin, n_clu <= 32, H >= h, W >= w.
+ * Optional, fused (src/eval_segmentation.py:124-126,138-139; src/utils.py:219-229):
+ *   code_flip  the code of the horizontally flipped images: the kernel evaluates (code + flip(code_flip)) / 2 (flip-TTA);
+ *   label      [B][H][W] int64 / int32 / uint8 (label_bytes 8 / 4 / 1): UnsupervisedMetrics.update — the int64
+ *              confusion counts lin_confusion [n_lin][n_label_classes], clu_confusion [n_clu][n_label_classes] are
+ *              incremented at [pred][actual] for every pixel with 0 <= label < n_label_classes and pred < n_label_classes.
  * ---------------------------------------------------------------------------------------------- */
-STEGO_API int stego_eval_probes(const float* code, long long ld_code, int C, int B, int h, int w, int H, int W,
-                                const float* lin_weight, const float* lin_bias, int n_lin, const float* clusters,
-                                int n_clu, float alpha, float* lr_scratch, float* lin_log_probs,
+STEGO_API int stego_eval_probes(const float* code, const float* code_flip, long long ld_code, int C, int B, int h, int w,
+                                int H, int W, const float* lin_weight, const float* lin_bias, int n_lin,
+                                const float* clusters, int n_clu, float alpha, float* lr_scratch, float* lin_log_probs,
                                 float* clu_log_probs, unsigned char* lin_argmax, unsigned char* clu_argmax,
-                                void* stream);
+                                const void* label, int label_bytes, int n_label_classes, long long* lin_confusion,
+                                long long* clu_confusion, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * k-nearest-neighbour descriptors (src/precompute_knns.py:15-21, 83-96):

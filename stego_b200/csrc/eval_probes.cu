@@ -11,6 +11,11 @@
 //     entries between neighbouring low-res pixels (self, right, down, down-right, down-left).
 // Two kernels: a per-low-res-pixel preparation (warp per pixel) and the per-output-pixel evaluation, which is
 // bound by writing the two [B,n,H,W] fp32 log-probability maps (HBM): 453 MB per 1024x2048 image.
+// Also fused here (src/eval_segmentation.py:124-126, 138-139; src/utils.py:219-229):
+//   * flip test-time augmentation  code = (code(img) + code(img.flip(3)).flip(3)) / 2  — averaged on the low-res code
+//     inside the preparation kernel (interpolation is linear, and the reference averages before it as well);
+//   * UnsupervisedMetrics.update for both probes: the [pred][actual] confusion counts are accumulated per CTA in shared
+//     memory from the argmax the kernel already has, one 64-bit atomic per non-zero cell per CTA.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -21,6 +26,7 @@ constexpr int EV_SS = 64, EV_R = 65, EV_D = 66, EV_DR = 67, EV_DL = 68;
 
 struct EvalPrepParams {
   const float* code;   // [B*h*w][ld] tokens-major
+  const float* code_flip;  // code of the horizontally flipped image (same layout) or null: flip-TTA average
   long long ld;
   int B, h, w, C;
   const float* W;      // [n_lin][C]
@@ -58,6 +64,8 @@ eval_prep_kernel(EvalPrepParams p) {
     const int x = static_cast<int>(r % p.w);
     const int y = static_cast<int>((r / p.w) % p.h);
     const float* cp = p.code + r * p.ld;
+    // flipped image: its column w-1-x holds this pixel; moving right here is moving left there
+    const float* fp = p.code_flip ? p.code_flip + (r - x + (p.w - 1 - x)) * p.ld : nullptr;
     float xr[3], nr[3], nd[3], ndr[3], ndl[3];
     const bool hr = x + 1 < p.w, hd = y + 1 < p.h, hl = x > 0;
 #pragma unroll
@@ -69,6 +77,13 @@ eval_prep_kernel(EvalPrepParams p) {
       nd[k] = (ok && hd) ? cp[p.w * p.ld + c] : 0.f;
       ndr[k] = (ok && hd && hr) ? cp[(p.w + 1) * p.ld + c] : 0.f;
       ndl[k] = (ok && hd && hl) ? cp[(p.w - 1) * p.ld + c] : 0.f;
+      if (fp) {
+        xr[k] = 0.5f * (xr[k] + (ok ? fp[c] : 0.f));
+        nr[k] = 0.5f * (nr[k] + ((ok && hr) ? fp[c - p.ld] : 0.f));
+        nd[k] = 0.5f * (nd[k] + ((ok && hd) ? fp[p.w * p.ld + c] : 0.f));
+        ndr[k] = 0.5f * (ndr[k] + ((ok && hd && hr) ? fp[(p.w - 1) * p.ld + c] : 0.f));
+        ndl[k] = 0.5f * (ndl[k] + ((ok && hd && hl) ? fp[(p.w + 1) * p.ld + c] : 0.f));
+      }
     }
     float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
 #pragma unroll
@@ -109,6 +124,11 @@ struct EvalProbeParams {
   unsigned char* lin_arg;  // [B][H][W] or null
   unsigned char* clu_arg;  // [B][H][W] or null
   int box_h, box_w;
+  const void* label;       // [B][H][W] int64 / int32 / uint8 (label_bytes 8 / 4 / 1) or null
+  int label_bytes;
+  int n_cls;               // label classes: a pixel counts when 0 <= label < n_cls and pred < n_cls (utils.py:222)
+  unsigned long long* lin_conf;  // [n_lin][n_cls] += counts of (pred, actual), or null
+  unsigned long long* clu_conf;  // [n_clu][n_cls]
 };
 
 __device__ __forceinline__ void ev_src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
@@ -138,6 +158,10 @@ __device__ __forceinline__ float ev_gram(const float* slr, int bw, int py, int p
 __global__ void __launch_bounds__(EVT_W* EVT_H)
 eval_probe_kernel(EvalProbeParams p) {
   extern __shared__ float slr[];  // [box_h*box_w][EV_LD]
+  __shared__ unsigned int hist[2][32 * 32];  // [probe][pred * 32 + actual]
+  const bool want_conf = p.label != nullptr;
+  if (want_conf)
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) (&hist[0][0])[i] = 0u;
   const int tiles_x = (p.W + EVT_W - 1) / EVT_W, tiles_y = (p.H + EVT_H - 1) / EVT_H;
   const int tile = blockIdx.x;
   const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
@@ -159,7 +183,9 @@ eval_probe_kernel(EvalProbeParams p) {
   }
   __syncthreads();
   const int X = X0 + (threadIdx.x % EVT_W), Y = Y0 + (threadIdx.x / EVT_W);
-  if (X >= p.W || Y >= p.H) return;
+  const bool active = X < p.W && Y < p.H;
+  int lin_pred = -1, clu_pred = -1;
+  if (active) {
   int y0, y1, x0, x1;
   float ly, lx;
   ev_src_index(Y, sy, p.h, y0, y1, ly);
@@ -184,6 +210,7 @@ eval_probe_kernel(EvalProbeParams p) {
         if (z[k] > mx) { mx = z[k]; arg = k; }
       }
     }
+    lin_pred = arg;
     if (p.lin_arg) p.lin_arg[b * plane + pix] = static_cast<unsigned char>(arg);
     if (p.lin_logp) {
       float se = 0.f;
@@ -214,6 +241,7 @@ eval_probe_kernel(EvalProbeParams p) {
         if (z[k] > mx) { mx = z[k]; arg = k; }
       }
     }
+    clu_pred = arg;
     if (p.clu_arg) p.clu_arg[b * plane + pix] = static_cast<unsigned char>(arg);
     if (p.clu_logp) {
       float m2 = -INFINITY;
@@ -231,6 +259,29 @@ eval_probe_kernel(EvalProbeParams p) {
         if (k < p.n_clu) o[k * plane] = z[k] * p.alpha - lse;
     }
   }
+  }  // active
+  if (want_conf) {
+    // UnsupervisedMetrics.update (src/utils.py:219-229): stats[pred][actual] += 1 over pixels with a valid label
+    if (active) {
+      const long long li = 1ll * b * p.H * p.W + 1ll * Y * p.W + X;
+      long long lab;
+      if (p.label_bytes == 8) lab = reinterpret_cast<const long long*>(p.label)[li];
+      else if (p.label_bytes == 4) lab = reinterpret_cast<const int*>(p.label)[li];
+      else lab = reinterpret_cast<const unsigned char*>(p.label)[li];
+      if (lab >= 0 && lab < p.n_cls) {
+        if (lin_pred >= 0 && lin_pred < p.n_cls) atomicAdd(&hist[0][lin_pred * 32 + static_cast<int>(lab)], 1u);
+        if (clu_pred >= 0 && clu_pred < p.n_cls) atomicAdd(&hist[1][clu_pred * 32 + static_cast<int>(lab)], 1u);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) {
+      const unsigned int cnt = (&hist[0][0])[i];
+      if (cnt == 0u) continue;
+      const int probe = i >> 10, pred = (i >> 5) & 31, act = i & 31;
+      unsigned long long* dst = probe ? p.clu_conf : p.lin_conf;
+      if (dst && act < p.n_cls && pred < (probe ? p.n_clu : p.n_lin)) atomicAdd(dst + pred * p.n_cls + act, (unsigned long long)cnt);
+    }
+  }
 }
 
 }  // namespace stego
@@ -238,19 +289,24 @@ eval_probe_kernel(EvalProbeParams p) {
 using namespace stego;
 
 // code: tokens-major low-res code [B*h*w][ld_code] fp32 (what DinoFeaturizer produces); outputs at [H][W].
-// lr_scratch: [B*h*w][72] floats.  Any output pointer may be null.
-extern "C" int stego_eval_probes(const float* code, long long ld_code, int C, int B, int h, int w, int H, int W,
-                                 const float* lin_weight, const float* lin_bias, int n_lin, const float* clusters,
-                                 int n_clu, float alpha, float* lr_scratch, float* lin_log_probs,
+// code_flip: the code of the horizontally flipped images (flip-TTA) or null.  lr_scratch: [B*h*w][72] floats.
+// label + confusion outputs (int64, accumulated): optional.  Any output pointer may be null.
+extern "C" int stego_eval_probes(const float* code, const float* code_flip, long long ld_code, int C, int B, int h, int w,
+                                 int H, int W, const float* lin_weight, const float* lin_bias, int n_lin,
+                                 const float* clusters, int n_clu, float alpha, float* lr_scratch, float* lin_log_probs,
                                  float* clu_log_probs, unsigned char* lin_argmax, unsigned char* clu_argmax,
-                                 void* stream_) {
+                                 const void* label, int label_bytes, int n_label_classes, long long* lin_confusion,
+                                 long long* clu_confusion, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STEGO_CHECK_ARG(code && lin_weight && lin_bias && clusters && lr_scratch, "stego_eval_probes: null pointer");
   STEGO_CHECK_ARG(C > 0 && C <= 96 && n_lin > 0 && n_lin <= 32 && n_clu > 0 && n_clu <= 32,
                   "stego_eval_probes: C=%d n_lin=%d n_clu=%d unsupported (C <= 96, classes <= 32)", C, n_lin, n_clu);
   STEGO_CHECK_ARG(B > 0 && h > 0 && w > 0 && H >= h && W >= w, "stego_eval_probes: bad sizes (upsampling only)");
+  STEGO_CHECK_ARG(!label || ((label_bytes == 8 || label_bytes == 4 || label_bytes == 1) && n_label_classes > 0 &&
+                             n_label_classes <= 32 && (lin_confusion || clu_confusion)),
+                  "stego_eval_probes: confusion counts need label_bytes in {8,4,1}, n_label_classes <= 32 and an output");
   EvalPrepParams q;
-  q.code = code; q.ld = ld_code; q.B = B; q.h = h; q.w = w; q.C = C; q.W = lin_weight; q.bias = lin_bias;
+  q.code = code; q.code_flip = code_flip; q.ld = ld_code; q.B = B; q.h = h; q.w = w; q.C = C; q.W = lin_weight; q.bias = lin_bias;
   q.n_lin = n_lin; q.clusters = clusters; q.n_clu = n_clu; q.lr = lr_scratch;
   const long long rows = 1ll * B * h * w;
   long long g = (rows + 7) / 8;
@@ -260,6 +316,9 @@ extern "C" int stego_eval_probes(const float* code, long long ld_code, int C, in
   EvalProbeParams p;
   p.lr = lr_scratch; p.B = B; p.h = h; p.w = w; p.H = H; p.W = W; p.n_lin = n_lin; p.n_clu = n_clu; p.alpha = alpha;
   p.lin_logp = lin_log_probs; p.clu_logp = clu_log_probs; p.lin_arg = lin_argmax; p.clu_arg = clu_argmax;
+  p.label = label; p.label_bytes = label_bytes; p.n_cls = n_label_classes;
+  p.lin_conf = reinterpret_cast<unsigned long long*>(lin_confusion);
+  p.clu_conf = reinterpret_cast<unsigned long long*>(clu_confusion);
   p.box_h = (int)((double)EVT_H * h / H) + 3;
   p.box_w = (int)((double)EVT_W * w / W) + 3;
   if (p.box_h > h) p.box_h = h;

@@ -103,6 +103,82 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Final LayerNorm fused with the global average pool of src/precompute_knns.py:19
+//     feats = model(img).mean([2, 3])          (model(img) = norm(x)[:, 1:] viewed as [B, E, h, w], src/modules.py:97)
+// One CTA of 8 warps per (image, chunk of patch tokens): every warp normalises its rows (cls token skipped) and keeps
+// per-channel running sums in registers; the CTA reduces them through shared memory and adds sum / (ntok - 1) to
+// out[b][E] with one atomic per channel.  The [B, hw, E] feature map is never written.
+// ---------------------------------------------------------------------------------------------
+template <int V4>
+__global__ void __launch_bounds__(256)
+layernorm_gap_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* __restrict__ out, int ntok, float eps, int rows_per_cta) {
+  constexpr int E = V4 * 128;
+  __shared__ float4 red[8][V4 * 32];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = 1 + blockIdx.x * rows_per_cta;  // token 0 is the cls token
+  const int t1 = min(ntok, t0 + rows_per_cta);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 g[V4], acc[V4];
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    g[i] = __ldg(g4 + lane + 32 * i);
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int nrows = 0;
+  for (int t = t0 + warp; t < t1; t += 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (1ll * b * ntok + t) * E);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bq * bq) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {  // beta is added once per row at the end (rows counted in nrows)
+      acc[i].x += (v[i].x - mean) * rstd * g[i].x;
+      acc[i].y += (v[i].y - mean) * rstd * g[i].y;
+      acc[i].z += (v[i].z - mean) * rstd * g[i].z;
+      acc[i].w += (v[i].w - mean) * rstd * g[i].w;
+    }
+    ++nrows;
+  }
+#pragma unroll
+  for (int i = 0; i < V4; ++i) red[warp][lane + 32 * i] = acc[i];
+  __shared__ int cnt[8];
+  if (lane == 0) cnt[warp] = nrows;
+  __syncthreads();
+  const float inv = 1.0f / (ntok - 1);
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) total += cnt[w];
+  for (int c4 = threadIdx.x; c4 < V4 * 32; c4 += blockDim.x) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 r = red[w][c4];
+      sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+    }
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float* o = out + 1ll * b * E + 4 * c4;
+    atomicAdd(o + 0, (sum.x + total * bb.x) * inv);
+    atomicAdd(o + 1, (sum.y + total * bb.y) * inv);
+    atomicAdd(o + 2, (sum.z + total * bb.z) * inv);
+    atomicAdd(o + 3, (sum.w + total * bb.w) * inv);
+  }
+}
+
 }  // namespace stego
 
 using namespace stego;
@@ -168,5 +244,24 @@ extern "C" int stego_layernorm_bf16(const float* x, const float* gamma, const fl
       return STEGO_ERR_UNSUPPORTED;
   }
   STEGO_CHECK_LAUNCH("layernorm_kernel");
+  return STEGO_OK;
+}
+
+// Final norm + GAP over the patch tokens (cls dropped): x fp32 [B][ntok][E] -> out fp32 [B][E] (zeroed by the caller).
+extern "C" int stego_layernorm_gap(const float* x, const float* gamma, const float* beta, float* out, int B, int ntok,
+                                   int E, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STEGO_CHECK_ARG(x && gamma && beta && out && B > 0 && ntok > 1, "stego_layernorm_gap: bad args");
+  const int rows_per_cta = 64;
+  dim3 grid((ntok - 1 + rows_per_cta - 1) / rows_per_cta, B);
+  switch (E) {
+    case 384: layernorm_gap_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, out, ntok, eps, rows_per_cta); break;
+    case 768: layernorm_gap_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, out, ntok, eps, rows_per_cta); break;
+    case 128: layernorm_gap_kernel<1><<<grid, 256, 0, stream>>>(x, gamma, beta, out, ntok, eps, rows_per_cta); break;
+    default:
+      set_error("stego_layernorm_gap: embed dim %d unsupported (128, 384, 768)", E);
+      return STEGO_ERR_UNSUPPORTED;
+  }
+  STEGO_CHECK_LAUNCH("layernorm_gap_kernel");
   return STEGO_OK;
 }

@@ -268,6 +268,21 @@ class VisionTransformer(nn.Module):
         ops.layernorm(x, w["nw"], w["nb"], out, eps=self.norm.eps, drop_cls_ntok=N)
         return out.view(B, N - 1, self.embed_dim)
 
+    @torch.no_grad()
+    def pooled_patch_features(self, img: torch.Tensor) -> torch.Tensor:
+        """mean over the patch tokens of norm(last block) — `DinoFeaturizer(img)[0].mean([2, 3])` of
+        src/precompute_knns.py:19 — fp32 [B, E], with the final LayerNorm and the pooling in one kernel (the [B, hw, E]
+        feature map is never written)."""
+        from .. import _lib
+        B = img.shape[0]
+        x, _ = self.forward_tokens(img)
+        w = self._prepared()
+        out = torch.zeros(B, self.embed_dim, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().stego_layernorm_gap(_lib.ptr(x), _lib.ptr(w["nw"]), _lib.ptr(w["nb"]), _lib.ptr(out), B,
+                                                   x.shape[0] // B, self.embed_dim, float(self.norm.eps), _lib.stream()),
+                   "stego_layernorm_gap")
+        return out
+
     def _all_tokens(self, img: torch.Tensor, want_qkv: bool = False):
         B = img.shape[0]
         x, qkv = self.forward_tokens(img, want_qkv)

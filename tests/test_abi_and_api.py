@@ -111,3 +111,38 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU"):
         _lib.load()
+
+
+def test_unsupervised_metrics_match_reference_arithmetic():
+    """stego_b200.eval.UnsupervisedMetrics vs a direct restatement of src/utils.py:219-274 (bincount confusion, Hungarian,
+    mIoU / accuracy) on random predictions, with and without extra clusters."""
+    import numpy as np
+    import torch
+    from scipy.optimize import linear_sum_assignment
+    from stego_b200.eval import UnsupervisedMetrics
+    g = torch.Generator().manual_seed(0)
+    n = 6
+    target = torch.randint(-1, n + 1, (4, 17, 19), generator=g)
+    preds = (target.clamp(0, n - 1) + (torch.rand(4, 17, 19, generator=g) < 0.3).long() * 2) % n
+    perm = torch.randperm(n, generator=g)
+    m = UnsupervisedMetrics("test/", n, 0, True)
+    m.update(perm[preds], target)
+    m.update(perm[preds], target)
+    out = m.compute()
+    mask = (target >= 0) & (target < n)
+    stats = torch.zeros(n, n, dtype=torch.int64)
+    for p_, a_ in zip(perm[preds][mask].tolist(), target[mask].tolist()):
+        stats[p_, a_] += 2
+    assert torch.equal(m.stats, stats)
+    rows, cols = linear_sum_assignment(stats, maximize=True)
+    hist = stats[np.argsort(cols), :].double()
+    tp = torch.diag(hist)
+    iou = tp / (hist.sum(0) + hist.sum(1) - tp)
+    assert abs(out["test/mIoU"] - 100 * iou[~torch.isnan(iou)].mean().item()) < 1e-9
+    assert abs(out["test/Accuracy"] - 100 * (tp.sum() / hist.sum()).item()) < 1e-9
+    lin = UnsupervisedMetrics("lin/", n, 0, False)
+    lin.update(preds, target)
+    assert 0 < lin.compute()["lin/Accuracy"] <= 100
+    ex = UnsupervisedMetrics("ex/", n, 2, True)
+    ex.update(preds, target)
+    assert ex.stats.shape == (n + 2, n) and "ex/mIoU" in ex.compute()

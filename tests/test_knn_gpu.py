@@ -45,3 +45,44 @@ def test_knn_rejects_bad_shapes(cuda_dev):
         knn_topk(torch.zeros(100, 100, device=cuda_dev), 5)
     with pytest.raises(RuntimeError, match="k="):
         knn_topk(torch.zeros(100, 64, device=cuda_dev), 40)
+
+
+def test_knn_descriptors_fused_layernorm_gap(cuda_dev):
+    """precompute_knns.py:19 `model(img).mean([2, 3])`: the fused final-LayerNorm + pooling kernel against pooling the
+    feature map DinoFeaturizer returns, eval and train mode (the reference never calls .eval(): Dropout2d is live)."""
+    import torch
+    from stego_b200.config import make_cfg
+    from stego_b200.knn import knn_descriptors, nns_file_name, precompute_knns, save_nns
+    from stego_b200.modules import DinoFeaturizer
+    cfg = make_cfg(random_backbone_init=True)
+    torch.manual_seed(0)
+    net = DinoFeaturizer(70, cfg).to(cuda_dev)
+    img = torch.randn(5, 3, 64, 96, device=cuda_dev)
+    net.eval()
+    with torch.no_grad():
+        want = net(img)[0].mean([2, 3])
+        got = knn_descriptors(net, img)
+    assert got.shape == (5, 384)
+    assert ((got - want).norm() / want.norm()).item() < 2e-3  # the feature map path rounds tokens to bf16 first
+    net.train()
+    torch.manual_seed(11)
+    with torch.no_grad():
+        want_t = net(img)[0].mean([2, 3])
+    st = torch.cuda.get_rng_state(cuda_dev)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        got_t = knn_descriptors(net, img)
+    assert ((got_t - want_t).norm() / want_t.norm()).item() < 2e-3
+    assert (got_t == 0).float().mean().item() > 0.05  # ~10 % of the channels dropped
+    # end to end: descriptors of a small image set -> top-k -> the .npz ContrastiveSegDataset loads
+    net.eval()
+    batches = [dict(img=torch.randn(4, 3, 64, 64)) for _ in range(3)]
+    idx = precompute_knns(net, batches, k=5)
+    assert idx.shape == (12, 5) and torch.equal(idx[:, 0].cpu(), torch.arange(12))
+    import numpy as np
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, nns_file_name("vit_small", "cocostuff27", "train", None, 224))
+        save_nns(path, idx)
+        loaded = np.load(path)["nns"]
+        assert loaded.dtype == np.int64 and loaded.shape == (12, 5) and (loaded == idx.cpu().numpy()).all()

@@ -63,3 +63,44 @@ def test_oracle_training_step_matches_reference_training_step():
         p = p0[k].clone()
         O.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1, 5e-4 if k.startswith("net.") else 5e-3)
         assert (params[k].detach() - p).abs().max().item() < 1e-7, k
+
+
+def test_knn_oracle_matches_lifted_reference_lines():
+    """The kNN restatement (oracle knn_descriptors / knn_indices) against the reference's own statements: `get_feats`
+    (src/precompute_knns.py:15-21) and the slab loop (:83-92), lifted as TEXT from the reference file and executed."""
+    import ast
+    import textwrap
+    import lightning_harness as H
+    import stego_oracle as O
+    src_dir = H.reference_src()
+    if src_dir is None:
+        pytest.skip("reference sources not present")
+    text = open(os.path.join(src_dir, "precompute_knns.py")).read()
+    tree = ast.parse(text)
+    get_feats_src = next(ast.get_source_segment(text, n) for n in tree.body
+                         if isinstance(n, ast.FunctionDef) and n.name == "get_feats")
+    lines = text.splitlines()
+    first = next(i for i, l in enumerate(lines) if "normed_feats = get_feats(par_model, loader)" in l)
+    last = next(i for i, l in enumerate(lines) if "nearest_neighbors = torch.cat(all_nns, dim=0)" in l)
+    loop_src = textwrap.dedent("\n".join(lines[first:last + 1]))
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    feats_maps = [torch.randn(8, 32, 5, 5, generator=g) for _ in range(5)]  # "model outputs" of 5 loader batches: n = 40
+    it = iter(feats_maps)
+    env = dict(torch=torch, F=F, tqdm=lambda x: x, n_batches=4)
+    orig_cuda, orig_empty = torch.Tensor.cuda, torch.cuda.empty_cache
+    torch.Tensor.cuda = lambda self, *a, **k: self  # get_feats moves the batch to the GPU; this is a CPU test
+    torch.cuda.empty_cache = lambda: None
+    try:
+        exec(get_feats_src, env)
+        env["par_model"] = type("ParModel", (), {"forward": staticmethod(lambda img: next(it))})()
+        env["loader"] = [dict(img=torch.zeros(8, 3, 4, 4)) for _ in feats_maps]
+        exec(loop_src, env)
+    finally:
+        torch.Tensor.cuda, torch.cuda.empty_cache = orig_cuda, orig_empty
+    want_feats, want_nn = env["normed_feats"], env["nearest_neighbors"]
+    desc = torch.cat([O.knn_descriptors(f) for f in feats_maps], 0)
+    assert torch.allclose(desc, want_feats, atol=1e-7)
+    idx, _ = O.knn_indices(desc, k=30, n_batches=4)
+    assert idx.shape == want_nn.shape == (40, 30)
+    assert torch.equal(idx, want_nn)
