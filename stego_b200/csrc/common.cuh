@@ -64,13 +64,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  // with a suspend-time hint the thread really sleeps until the phase completes (or the hint expires): without it
+  // try_wait came back every few hundred cycles and the retry loops of waiting warps executed ~20 % of all instructions
+  // of the attention kernel (ncu source counters: 1.8 M YIELD iterations), competing with the warps doing the work
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P1;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -100,13 +103,15 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // Blocking wait with a watchdog: if a pipeline bug deadlocks the CTA we trap (launch error on the
 // host) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // non-blocking probe first: try_wait is a potentially-suspending instruction and costs ~200 cycles even when the phase
+  // completed long ago (clock64 stamps, profiles/r2_attn_trace.md); most waits of a well-fed pipeline end right here
+  if (mbar_test_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
-  // try_wait suspends the thread for a hardware time slice by itself; keep the retry loop to two instructions and
-  // consult the (expensive) global timer only every 64K retries.
+  // try_wait suspends the thread by itself (up to its 1 ms hint); consult the global timer only every 64 retries.
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFFu) == 0) {
+    if ((++spins & 0x3Fu) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) {
         t0 = now;
@@ -309,6 +314,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// the same, volatile: a run of these keeps its program order (used to issue a batch of independent MUFUs back to back)
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
 
