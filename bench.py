@@ -437,6 +437,49 @@ def kernel_rooflines(cfgd, peaks, dev):
 
 
 # ----------------------------------------------------------------------------------------------------
+# dense correlation sweep (SURVEY.md §8d "dense stress variant", labelled NON-REFERENCE: the reference samples S = 121
+# points per image; S = h w is its plotting script's use of the same einsum, src/plot_dino_correspondence.py:45,49)
+# ----------------------------------------------------------------------------------------------------
+def run_corr_sweep(args):
+    """`tensor_correlation` (einsum nchw,ncij->nhwij) as one batched tcgen05 GEMM launch, S x S x E per image, for S from
+    the reference's 121 sampled points up to the full feature map of c1 / c2 / c3.  TFLOP/s are ALGORITHMIC (2 S^2 E per
+    image) against the measured bf16 peak; `split3` is the fp32-input path (bf16 hi/lo split: 3x the tensor work for
+    ~2^-16 relative error), `bf16` the single pass on bf16 features (what the frozen backbone emits)."""
+    from stego_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    rows = []
+    for name, E, S, B in [("S=121 (reference: 11x11 samples), ViT-S", 384, 121, 32), ("S=121, ViT-B", 768, 121, 32),
+                          ("S=400", 384, 400, 32), ("S=784 = 28x28 (c1 dense)", 384, 784, 32),
+                          ("S=1600 = 40x40 (c2 dense)", 768, 1600, 32), ("S=3136 = 56x56 (c3 dense)", 768, 3136, 16)]:
+        g = torch.Generator(device=dev).manual_seed(S)
+        f = torch.nn.functional.normalize(torch.randn(B, S, E, device=dev, generator=g), dim=2)
+        ld = (S + 3) // 4 * 4
+        out = torch.empty(B, S, ld, device=dev)
+        res = {}
+        for mode in ("bf16", "split3"):
+            if mode == "bf16":
+                a = f.bfloat16().contiguous()
+                b = a
+            else:
+                hi = f.bfloat16()
+                lo = (f - hi.float()).bfloat16()
+                a = torch.cat([hi, lo, hi], 2).contiguous()
+                b = torch.cat([hi, hi, lo], 2).contiguous()
+            ms = time_kernel(lambda: ops.gemm_batched(a, b, out[:, :, :S]), flush=flush)
+            fl = 2.0 * B * S * S * E
+            res[mode] = {"ms": ms, "algorithmic_tflops": fl / ms / 1e9, "frac_of_bf16_peak": fl / ms / 1e9 / peaks["tf_burst"],
+                         "tensor_work_tflops": fl * (3 if mode == "split3" else 1) / ms / 1e9}
+        want = torch.einsum("nsc,ntc->nst", f[:2].double(), f[:2].double())
+        err = (out[:2, :, :S].double() - want).abs().max().item()
+        rows.append({"case": name, "E": E, "S": S, "images": B, "max_abs_err_split3_vs_fp64": err, **res})
+    print(json.dumps({"metric": "correlation-einsum TFLOP/s vs bf16 peak (dense sweep, NON-REFERENCE sizes beyond S=121)",
+                      "peak_tflops": peaks["tf_burst"], "peak_source": peaks["source"] + ", burst", "rows": rows}))
+
+
+# ----------------------------------------------------------------------------------------------------
 # configs[4]: fused eval probes (HBM-bound; metric frames/s)
 # ----------------------------------------------------------------------------------------------------
 def run_c4(args, rank, world, local):
@@ -578,6 +621,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also report per-phase device time of the step")
+    ap.add_argument("--corr-sweep", action="store_true", help="dense tensor_correlation sweep (S = 121 ... h w) and exit")
     args = ap.parse_args()
     cfgd = dict(CONFIGS[args.config])
     if args.batch:
@@ -585,6 +629,8 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.corr_sweep:
+        return run_corr_sweep(args) if rank == 0 else None
     if args.config == "c4":
         return run_c4(args, rank, world, local)
     model_type, res, B = cfgd["model_type"], cfgd["res"], cfgd["batch"]
@@ -625,6 +671,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the one collective is a <= 2.8 MB all-reduce that runs on a side stream UNDER the next step's frozen backbone:
+        # two channels are plenty for it, and every SM NCCL does not occupy stays with the persistent GEMM / attention CTAs
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     from stego_b200 import _lib
     from stego_b200.config import make_cfg

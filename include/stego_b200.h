@@ -53,6 +53,16 @@ STEGO_API int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void
                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
                               void* stream);
 
+/* `batch` independent GEMMs of one shape in ONE launch: entry b reads A + b * a_batch_stride, B + b * b_batch_stride and
+ * writes out + b * out_batch_stride (strides in elements; operand strides multiples of 8).  Rows past M / N of an entry
+ * are zero-filled / clipped by TMA, so M and N need not be tile multiples.  This is `tensor_correlation`
+ * (src/modules.py:283-284: einsum nchw,ncij->nhwij = one [hw, C] x [C, ij] GEMM per image) for ANY h w, i j — the dense
+ * S = h w case of SURVEY.md 8(d) included — with the bf16 hi/lo split folded into K ([hi | lo | hi] . [hi | hi | lo]). */
+STEGO_API int stego_gemm_bf16_batched(const void* A, int lda, long long a_batch_stride, int a_mn_major, const void* B,
+                                      int ldb, long long b_batch_stride, int b_mn_major, int batch, int M, int N, int K,
+                                      void* out, int ldo, long long out_batch_stride, int out_bf16, const float* bias,
+                                      int act, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Frozen DINO ViT forward pieces (reference: src/dino/vision_transformer.py)
  * ---------------------------------------------------------------------------------------------- */

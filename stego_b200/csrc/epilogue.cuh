@@ -94,7 +94,8 @@ struct EpiArgs {
 
 template <int BN, uint32_t kEpiBufs, int kParts>
 __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const EpiArgs& p, uint32_t taddr, uint8_t* buf0,
-                                                  uint32_t& epi_groups, int part, int lane, int col_tile0, int row_base) {
+                                                  uint32_t& epi_groups, int part, int lane, int col_tile0, int row_base,
+                                                  int batch_idx) {
   // kParts warps share one TMEM lane quarter and take every kParts-th column group.  32 accumulator columns are in
   // registers at a time (the kernel runs 18 warps: 112 registers per thread).
   if (p.out_bf16) {
@@ -141,7 +142,7 @@ __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(buf, tmO, col0, row_base);
+        tma_store_3d(buf, tmO, col0, row_base, batch_idx);
         tma_commit_group();
       }
       ++epi_groups;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const 
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-      if (p.bias != nullptr) {
+      if (p.bias != nullptr) {  // (callers only route N % 32 != 0 here without a bias: the store clips, a bias load would not)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
@@ -181,8 +182,8 @@ __device__ __forceinline__ void epilogue_tma_tile(const CUtensorMap* tmO, const 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (p.reduce_add) tma_reduce_add_2d(buf, tmO, col0, row_base);
-        else tma_store_2d(buf, tmO, col0, row_base);
+        if (p.reduce_add) tma_reduce_add_3d(buf, tmO, col0, row_base, batch_idx);
+        else tma_store_3d(buf, tmO, col0, row_base, batch_idx);
         tma_commit_group();
       }
       ++epi_groups;

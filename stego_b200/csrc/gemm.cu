@@ -53,6 +53,9 @@ struct GemmParams {
   int vec_ok;         // host-verified 16-byte alignment of out/residual rows
   int fast_epi;       // coalesced smem-transpose epilogue usable (aligned, N % 32 == 0 tiles, plain row mapping)
   int tma_epi;        // 1: epilogue tiles leave through TMA stores; 2: TMA fp32 reduce-add (in-place residual)
+  int batch;          // independent GEMMs of the same shape (third tensor-map dimension); 1 = plain GEMM
+  long long out_bs;   // element stride between the outputs / residuals of consecutive batch entries
+  long long res_bs;
   int diag;           // -DSTEGO_DIAG builds only: STEGO_GEMM_DIAG bit flags for phase timing (results are garbage):
                       // 1 skip the epilogue work, 2 skip the MMAs, 4 skip the TMA loads
 };
@@ -97,7 +100,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_m = tiles_m_real;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;  // K tail: TMA zero-fills out-of-bounds
-  const int total_tiles = tiles_m * tiles_n * p.splits;
+  const int tiles_per_batch = tiles_m * tiles_n * p.splits;
+  const int total_tiles = tiles_per_batch * p.batch;
   const int sched_start = static_cast<int>(blockIdx.x);
   const int sched_step = static_cast<int>(gridDim.x);
 
@@ -126,9 +130,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0 && !GEMM_DIAG(p, 4)) {
       uint32_t stage = 0, phase = 0;
       for (int t = sched_start; t < total_tiles; t += sched_step) {
-        const int split = t % p.splits;
-        const int tn = (t / p.splits) % tiles_n;
-        const int tm = t / (p.splits * tiles_n);
+        const int tb = t / tiles_per_batch, tl = t % tiles_per_batch;
+        const int split = tl % p.splits;
+        const int tn = (tl / p.splits) % tiles_n;
+        const int tm = tl / (p.splits * tiles_n);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -137,20 +142,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, tm * GEMM_BM);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, tm * GEMM_BM, tb);
           } else {
 #pragma unroll
             for (int blk = 0; blk < GEMM_BM / 64; ++blk)
-              tma_load_2d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK);
+              tma_load_3d(sa + blk * 8192, &tmA, &full_bar[stage], tm * GEMM_BM + blk * 64, kb * GEMM_BK, tb);
           }
           if (!B_MN) {
 #pragma unroll
             for (int blk = 0; blk < BN / kBBox; ++blk)  // tensor-map box = kBBox rows
-              tma_load_2d(sb + blk * (kBBox * 128), &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * kBBox);
+              tma_load_3d(sb + blk * (kBBox * 128), &tmB, &full_bar[stage], kb * GEMM_BK, tn * BN + blk * kBBox, tb);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / 64; ++blk)
-              tma_load_2d(sb + blk * 8192, &tmB, &full_bar[stage], tn * BN + blk * 64, kb * GEMM_BK);
+              tma_load_3d(sb + blk * 8192, &tmB, &full_bar[stage], tn * BN + blk * 64, kb * GEMM_BK, tb);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -171,7 +176,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? 8192u : 16u);
     const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192u : 16u);
     for (int t = sched_start; t < total_tiles; t += sched_step) {
-      const int split = t % p.splits;
+      const int split = (t % tiles_per_batch) % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(num_kb, kb0 + p.kb_per_split);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -207,16 +212,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     uint32_t epi_groups = 0;  // bulk-store groups this warp has committed (selects the staging tile)
     for (int t = sched_start; t < total_tiles; t += sched_step) {
-      const int tn = (t / p.splits) % tiles_n;
-      const int tm = t / (p.splits * tiles_n);
-      if (p.fast_epi && !p.tma_epi && p.residual != nullptr) {
+      const int tb = t / tiles_per_batch, tl = t % tiles_per_batch;
+      const int tn = (tl / p.splits) % tiles_n;
+      const int tm = tl / (p.splits * tiles_n);
+      // batch entry of this tile: outputs / residuals of consecutive entries are out_bs / res_bs elements apart
+      void* const outp = p.out_bf16 ? static_cast<void*>(reinterpret_cast<bf16*>(p.out) + tb * p.out_bs)
+                                    : static_cast<void*>(reinterpret_cast<float*>(p.out) + tb * p.out_bs);
+      const float* const resp = p.residual ? p.residual + tb * p.res_bs : nullptr;
+      if (p.fast_epi && !p.tma_epi && resp != nullptr) {
         // pull this warp's slice of the residual tile towards L2 while the MMAs of the tile are still running
         const int prow = tm * GEMM_BM + quarter * 32 + lane;
         if (prow < p.M) {
           for (int c = half; c < BN / 32; c += kParts) {
             const int pc = tn * BN + c * 32;
             if (pc < p.N)
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.residual + static_cast<size_t>(prow) * p.ldr + pc));
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(resp + static_cast<size_t>(prow) * p.ldr + pc));
           }
         }
       }
@@ -244,7 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         EpiArgs ea;
         ea.bias = p.bias; ea.act = p.act; ea.out_bf16 = p.out_bf16; ea.reduce_add = (p.tma_epi == 2); ea.N = p.N;
         epilogue_tma_tile<BN, kEpiBufs, kParts>(&tmO, ea, taddr, epi_smem + (warp - 2) * (kEpiBufs * 4096), epi_groups, half,
-                                                lane, tn * BN, tm * GEMM_BM + quarter * 32);
+                                                lane, tn * BN, tm * GEMM_BM + quarter * 32, tb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -305,7 +315,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int grow = row_base + r;
               if (grow < p.M && col < p.N) {
                 const uint4 w = *reinterpret_cast<const uint4*>(buf + sw128_offset(r, chunk));
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(grow) * p.ldo + col) = w;
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(outp) + static_cast<size_t>(grow) * p.ldo + col) = w;
               }
             }
             __syncwarp();
@@ -319,12 +329,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // all residual loads first (out may alias residual: the compiler cannot hoist loads over the stores,
             // so issuing them together is what keeps 8 x 512 B per warp in flight instead of one)
             float4 rr[8];
-            if (p.residual != nullptr) {
+            if (resp != nullptr) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int grow = row_base + i * 4 + rsub;
                 rr[i] = (grow < p.M && col < p.N)
-                            ? *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col)
+                            ? *reinterpret_cast<const float4*>(resp + static_cast<size_t>(grow) * p.ldr + col)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
               }
             } else {
@@ -363,7 +373,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (grow < p.M && col < p.N) {
                 float4 y = *reinterpret_cast<const float4*>(buf + sw128_offset(r, chunk));
                 y.x += rr[i].x; y.y += rr[i].y; y.z += rr[i].z; y.w += rr[i].w;
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + col) = y;
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(outp) + static_cast<size_t>(grow) * p.ldo + col) = y;
               }
             }
             __syncwarp();
@@ -401,15 +411,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
         }
         if (p.atomic) {
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0;
+          float* o = reinterpret_cast<float*>(outp) + static_cast<size_t>(out_row) * p.ldo + col0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (full || col0 + j < p.N) atomicAdd(o + j, x[j]);
           continue;
         }
         if (full && p.vec_ok) {
-          if (p.residual != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(res_row) * p.ldr + col0);
+          if (resp != nullptr) {
+            const float4* r4 = reinterpret_cast<const float4*>(resp + static_cast<size_t>(res_row) * p.ldr + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r = r4[j];
@@ -417,7 +427,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0);
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(outp) + static_cast<size_t>(out_row) * p.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
@@ -428,7 +438,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[j] = w;
             }
           } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.ldo + col0);
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(outp) + static_cast<size_t>(out_row) * p.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           }
@@ -437,11 +447,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) {
             if (col0 + j < p.N) {
               float y = x[j];
-              if (p.residual != nullptr) y += p.residual[static_cast<size_t>(res_row) * p.ldr + col0 + j];
+              if (resp != nullptr) y += resp[static_cast<size_t>(res_row) * p.ldr + col0 + j];
               if (p.out_bf16)
-                reinterpret_cast<bf16*>(p.out)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = __float2bfloat16_rn(y);
+                reinterpret_cast<bf16*>(outp)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = __float2bfloat16_rn(y);
               else
-                reinterpret_cast<float*>(p.out)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = y;
+                reinterpret_cast<float*>(outp)[static_cast<size_t>(out_row) * p.ldo + col0 + j] = y;
             }
           }
         }
@@ -476,7 +486,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles = tiles_m * tiles_n * p.splits;
+  const int tiles = tiles_m * tiles_n * p.splits * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, gemm_threads(BN), smem, stream>>>(tmA, tmB, tmO, p);
   STEGO_CHECK_LAUNCH("gemm_bf16_kernel launch");
@@ -487,19 +497,29 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 using namespace stego;
 
-// C-ABI: see include/stego_b200.h for the contract.
-extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
-                               int N, int K, void* out, int ldo, int out_bf16, const float* bias, int act,
-                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
-                               void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// Shared implementation of stego_gemm_bf16 (batch = 1) and stego_gemm_bf16_batched: `batch` independent GEMMs of one
+// shape, entry b reading A + b * a_bs, B + b * b_bs and writing out + b * out_bs (element strides); every tensor map
+// is 3-D with the batch as its outermost dimension, so rows past M / N of an entry are out of bounds for TMA (zero
+// fill on loads, clipped on stores) instead of running into the next entry.
+static int gemm_impl(const void* A, int lda, long long a_bs, int a_mn_major, const void* B, int ldb, long long b_bs,
+                     int b_mn_major, int batch, int M, int N, int K, void* out, int ldo, long long out_bs, int out_bf16,
+                     const float* bias, int act, const float* residual, int ldr, long long res_bs, int row_div, int splits,
+                     int atomic_out, cudaStream_t stream) {
   STEGO_CHECK_ARG(A && B && out, "stego_gemm_bf16: null pointer");
-  STEGO_CHECK_ARG(M > 0 && N > 0 && K > 0, "stego_gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
+  STEGO_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "stego_gemm_bf16: bad sizes M=%d N=%d K=%d batch=%d", M, N, K, batch);
   STEGO_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "stego_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  STEGO_CHECK_ARG(batch == 1 || (a_bs % 8 == 0 && b_bs % 8 == 0 && row_div == 0),
+                  "stego_gemm_bf16_batched: operand batch strides must be multiples of 8 elements");
   STEGO_CHECK_ARG(act >= 0 && act <= 2, "stego_gemm_bf16: act=%d", act);
   STEGO_CHECK_ARG(!(atomic_out && out_bf16), "stego_gemm_bf16: atomic output must be fp32");
   STEGO_CHECK_ARG(splits >= 1, "stego_gemm_bf16: splits=%d", splits);
   STEGO_CHECK_ARG(splits == 1 || atomic_out, "stego_gemm_bf16: split-K requires atomic_out");
+  if (batch == 1) {  // any 16-byte-compatible value: the third coordinate is always 0
+    a_bs = static_cast<long long>(a_mn_major ? K : M) * lda;
+    b_bs = static_cast<long long>(b_mn_major ? K : N) * ldb;
+    out_bs = static_cast<long long>(M) * ldo;
+    res_bs = 0;
+  }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -511,6 +531,7 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   p.bias = bias; p.act = act;
   p.residual = residual; p.ldr = ldr;
   p.row_div = row_div; p.atomic = atomic_out;
+  p.batch = batch; p.out_bs = out_bs; p.res_bs = res_bs;
   const size_t esz = out_bf16 ? 2 : 4;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((size_t(ldo) * esz) % 16 == 0) &&
              (residual == nullptr || (((reinterpret_cast<uintptr_t>(residual) & 15u) == 0) && (size_t(ldr) * 4) % 16 == 0));
@@ -521,10 +542,14 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
                !(out_bf16 && residual != nullptr);
   // TMA epilogue: plain store for outputs without a residual; fp32 reduce-add when the residual IS the output
   // (the in-place x += ... of the transformer blocks) — then the epilogue issues no global loads at all.
+  // Without a bias the TMA store also covers N % 32 != 0 (the tensor map clips the last column group), which is what
+  // the dense correlation (N = h w = 784, 1600, 3136) needs.
+  const bool tma_ragged_ok = p.vec_ok && !atomic_out && row_div == 0 && bias == nullptr && residual == nullptr &&
+                             (out_bs * static_cast<long long>(esz)) % 16 == 0;
   p.tma_epi = 0;
-  if (p.fast_epi && !b_mn_major && !a_mn_major) {
+  if ((p.fast_epi || tma_ragged_ok) && !b_mn_major && !a_mn_major && (out_bs * static_cast<long long>(esz)) % 16 == 0) {
     if (residual == nullptr) p.tma_epi = 1;
-    else if (!out_bf16 && residual == out && ldr == ldo) p.tma_epi = 2;
+    else if (!out_bf16 && residual == out && ldr == ldo && res_bs == out_bs) p.tma_epi = 2;
   }
   p.diag = 0;
 #ifdef STEGO_DIAG
@@ -547,23 +572,23 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   CUtensorMap tmA, tmB, tmO;
   int rc;
   {
-    // K-major: tensor is [M][K] (inner = K). MN-major: tensor is [K][M] (inner = M).
-    uint64_t dims[2] = {a_mn_major ? (uint64_t)M : (uint64_t)K, a_mn_major ? (uint64_t)K : (uint64_t)M};
-    uint64_t str[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {64, a_mn_major ? 64u : (uint32_t)GEMM_BM};
-    if ((rc = make_tmap_bf16(&tmA, A, 2, dims, str, box)) != STEGO_OK) return rc;
+    // K-major: tensor is [batch][M][K] (inner = K). MN-major: tensor is [batch][K][M] (inner = M).
+    uint64_t dims[3] = {a_mn_major ? (uint64_t)M : (uint64_t)K, a_mn_major ? (uint64_t)K : (uint64_t)M, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)a_bs * 2};
+    uint32_t box[3] = {64, a_mn_major ? 64u : (uint32_t)GEMM_BM, 1};
+    if ((rc = make_tmap_bf16(&tmA, A, 3, dims, str, box)) != STEGO_OK) return rc;
   }
   {
-    uint64_t dims[2] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N};
-    uint64_t str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, (b_mn_major || use_192) ? 64u : 128u};  // rows per B box: must match the kernel's kBBox
-    if ((rc = make_tmap_bf16(&tmB, B, 2, dims, str, box)) != STEGO_OK) return rc;
+    uint64_t dims[3] = {b_mn_major ? (uint64_t)N : (uint64_t)K, b_mn_major ? (uint64_t)K : (uint64_t)N, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)b_bs * 2};
+    uint32_t box[3] = {64, (b_mn_major || use_192) ? 64u : 128u, 1};  // rows per B box: must match the kernel's kBBox
+    if ((rc = make_tmap_bf16(&tmB, B, 3, dims, str, box)) != STEGO_OK) return rc;
   }
   if (p.tma_epi) {
-    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
-    uint64_t str[1] = {(uint64_t)ldo * esz};
-    uint32_t box[2] = {out_bf16 ? 64u : 32u, 32u};
-    rc = out_bf16 ? make_tmap_bf16(&tmO, out, 2, dims, str, box) : make_tmap_f32(&tmO, out, 2, dims, str, box);
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)ldo * esz, (uint64_t)out_bs * esz};
+    uint32_t box[3] = {out_bf16 ? 64u : 32u, 32u, 1};
+    rc = out_bf16 ? make_tmap_bf16(&tmO, out, 3, dims, str, box) : make_tmap_f32(&tmO, out, 3, dims, str, box);
     if (rc != STEGO_OK) return rc;
   } else {
     tmO = tmA;  // unused
@@ -575,4 +600,21 @@ extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   if (!a_mn_major && b_mn_major) return launch_gemm<128, 5, false, true>(tmA, tmB, tmO, p, stream);
   if (a_mn_major && b_mn_major) return launch_gemm<128, 5, true, true>(tmA, tmB, tmO, p, stream);
   return launch_gemm<128, 5, true, false>(tmA, tmB, tmO, p, stream);
+}
+
+// C-ABI: see include/stego_b200.h for the contract.
+extern "C" int stego_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
+                               int N, int K, void* out, int ldo, int out_bf16, const float* bias, int act,
+                               const float* residual, int ldr, int row_div, int splits, int atomic_out,
+                               void* stream_) {
+  return gemm_impl(A, lda, 0, a_mn_major, B, ldb, 0, b_mn_major, 1, M, N, K, out, ldo, 0, out_bf16, bias, act, residual, ldr, 0,
+                   row_div, splits, atomic_out, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int stego_gemm_bf16_batched(const void* A, int lda, long long a_batch_stride, int a_mn_major, const void* B,
+                                       int ldb, long long b_batch_stride, int b_mn_major, int batch, int M, int N, int K,
+                                       void* out, int ldo, long long out_batch_stride, int out_bf16, const float* bias,
+                                       int act, void* stream_) {
+  return gemm_impl(A, lda, a_batch_stride, a_mn_major, B, ldb, b_batch_stride, b_mn_major, batch, M, N, K, out, ldo,
+                   out_batch_stride, out_bf16, bias, act, nullptr, 0, 0, 0, 1, 0, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -52,34 +52,37 @@ def average_norm(t):
 
 
 def tensor_correlation(a, b):
-    """modules.py:283-284: einsum nchw,ncij->nhwij.  On CUDA the contraction runs on the tcgen05 GEMM
-    (bf16 hi/lo split operands, fp32 accumulate); off-device there is no implementation."""
+    """modules.py:283-284: einsum nchw,ncij->nhwij — one [hw, C] x [C, ij] GEMM per image, all images in ONE launch of
+    the batched tcgen05 GEMM.  fp32 inputs are split into bf16 hi + lo parts and the three significant products are
+    folded into the K axis: [hi | lo | hi] . [hi | hi | lo]^T = hi.hi + lo.hi + hi.lo (fp32 accumulate, ~2^-16
+    relative instead of bf16's 2^-9); bf16 inputs take a single pass.  Off-device there is no implementation."""
     if not (a.is_cuda and b.is_cuda):
         raise RuntimeError("stego_b200.tensor_correlation: CUDA tensors required (no CPU fallback)")
     n, c, h, w = a.shape
     _, _, i, j = b.shape
-    A = a.reshape(n, c, h * w).transpose(1, 2).float()  # [n, hw, c]
-    Bm = b.reshape(n, c, i * j).transpose(1, 2).float()  # [n, ij, c]
-    cp = _round_up(c, 64)
-    out = torch.empty(n, h * w, i * j, dtype=torch.float32, device=a.device)
+    exact_bf16 = a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    cp = _round_up(c, 8)
+    parts = 1 if exact_bf16 else 3
 
-    def split(x, rows):
-        buf = torch.zeros(n, rows, 2 * cp, dtype=torch.bfloat16, device=a.device)
+    def operand(x, rows, order):  # [n, rows, parts * cp] bf16, K-major
+        x = x.reshape(n, c, rows).transpose(1, 2)
+        buf = torch.zeros(n, rows, parts * cp, dtype=torch.bfloat16, device=x.device)
+        if exact_bf16:
+            buf[:, :, :c] = x
+            return buf
+        x = x.float()
         hi = x.to(torch.bfloat16)
-        buf[:, :, :c] = hi
-        buf[:, :, cp:cp + c] = (x - hi.float()).to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        for k, part in enumerate(order):
+            buf[:, :, k * cp:k * cp + c] = hi if part == "hi" else lo
         return buf
 
-    As, Bs = split(A, h * w), split(Bm, i * j)
-    for k in range(n):
-        # [hi | lo] . [hi | lo]^T over the concatenated K axis gives hi.hi + lo.lo; add the cross terms
-        a_hi, a_lo = As[k, :, :cp], As[k, :, cp:]
-        b_hi, b_lo = Bs[k, :, :cp], Bs[k, :, cp:]
-        o = out[k]
-        ops.gemm(a_hi, b_hi, o, M=h * w, N=i * j, K=cp)
-        ops.gemm(a_lo, b_hi, o, M=h * w, N=i * j, K=cp, residual=o)
-        ops.gemm(a_hi, b_lo, o, M=h * w, N=i * j, K=cp, residual=o)
-    return out.reshape(n, h, w, i, j)
+    A = operand(a, h * w, ("hi", "lo", "hi"))
+    Bm = operand(b, i * j, ("hi", "hi", "lo"))
+    ld = _round_up(i * j, 4)  # 16-byte rows for the TMA store of the fp32 result
+    out = torch.empty(n, h * w, ld, dtype=torch.float32, device=a.device)
+    ops.gemm_batched(A, Bm, out[:, :, :i * j])
+    return out[:, :, :i * j].reshape(n, h, w, i, j) if ld == i * j else out[:, :, :i * j].contiguous().reshape(n, h, w, i, j)
 
 
 def sample(t: torch.Tensor, coords: torch.Tensor):

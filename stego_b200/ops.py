@@ -38,6 +38,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     return out
 
 
+def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+                 bias: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> torch.Tensor:
+    """out[n] = act(A[n] . B[n]^T + bias) for every n in ONE launch (stego_gemm_bf16_batched).
+    a: [n, M, K] (or [n, K, M] if a_mn), b: [n, N, K] (or [n, K, N] if b_mn), bf16, inner dimension contiguous;
+    out: [n, M, N] fp32 or bf16."""
+    _lib.require_cuda(a, b, out, bias)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 3 and b.dim() == 3 and out.dim() == 3
+    assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    n = a.shape[0]
+    M, K = (a.shape[2], a.shape[1]) if a_mn else (a.shape[1], a.shape[2])
+    N = b.shape[2] if b_mn else b.shape[1]
+    assert b.shape[0] == n and out.shape == (n, M, N) and (b.shape[1] if b_mn else b.shape[2]) == K
+    rc = _lib.load().stego_gemm_bf16_batched(
+        _lib.ptr(a), a.stride(1), a.stride(0), int(a_mn), _lib.ptr(b), b.stride(1), b.stride(0), int(b_mn), n, M, N, K,
+        _lib.ptr(out), out.stride(1), out.stride(0), int(out.dtype == torch.bfloat16), _lib.ptr(bias), act, _lib.stream())
+    _lib.check(rc, "stego_gemm_bf16_batched")
+    return out
+
+
 def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
     """PatchEmbed im2col rows [B*hw, 3*p*p] bf16 (stego_vit_patchify / stego_vit_patchify_bf16)."""
     _lib.require_cuda(img)

@@ -59,11 +59,17 @@ def main():
         e = rel(g[k] / world, mean_g[k])
         worst_g = max(worst_g, e)
         ok &= e < 1e-5
+        # Adam's first step is sign-like (g / (|g| + eps)): elements with |g| ~ 1e-8 amplify the 2e-6 difference between
+        # the all-reduced gradient and the emulated mean, so the update is checked exactly against the all-reduced
+        # gradient (arithmetic + 1/world scale) and loosely against the emulated mean
+        want = p0[k].clone()
+        O.adam_step(want, g[k] / world, torch.zeros_like(want), torch.zeros_like(want), 1, lr_of(k))
+        ok &= rel(p1[k] - p0[k], want - p0[k]) < 1e-5
         want = p0[k].clone()
         O.adam_step(want, mean_g[k], torch.zeros_like(want), torch.zeros_like(want), 1, lr_of(k))
         e = rel(p1[k] - p0[k], want - p0[k])
         worst_p = max(worst_p, e)
-        ok &= e < 1e-4
+        ok &= e < 2e-3
     # the shards really differ (otherwise the test proves nothing)
     ok &= rel(shard_grads[0]["linear_probe.weight"], shard_grads[-1]["linear_probe.weight"]) > 1e-2
     # ---- 3. replicas stay identical

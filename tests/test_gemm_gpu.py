@@ -167,3 +167,24 @@ def _lib_gemm_raw(a, w, out, M, N, K, bias):
     from stego_b200 import _lib
     return _lib.load().stego_gemm_bf16(_lib.ptr(a), a.stride(0), 0, _lib.ptr(w), w.stride(0), 0, M, N, K, _lib.ptr(out),
                                        out.stride(0), 0, _lib.ptr(bias), 0, 0, 0, 0, 1, 0, _lib.stream())
+
+
+@pytest.mark.parametrize("n,M,N,K", [(3, 121, 121, 384), (2, 784, 784, 1152), (5, 50, 300, 72), (1, 128, 256, 64)])
+def test_gemm_batched_ragged(cuda_dev, n, M, N, K):
+    """stego_gemm_bf16_batched: independent GEMMs in one launch, M / N not tile multiples (TMA zero-fill / clipping per
+    batch entry), fp32 output with a 16-byte-aligned row pitch."""
+    from stego_b200 import ops
+    torch.manual_seed(n * 7 + M)
+    a = torch.randn(n, M, K, device=cuda_dev).bfloat16()
+    b = (torch.randn(n, N, K, device=cuda_dev) / K ** 0.5).bfloat16()
+    ld = (N + 3) // 4 * 4
+    store = torch.full((n, M, ld), float("nan"), device=cuda_dev)
+    ops.gemm_batched(a, b, store[:, :, :N])
+    want = torch.einsum("nmk,npk->nmp", a.float(), b.float())
+    assert torch.isfinite(store[:, :, :N]).all()
+    assert _rel(store[:, :, :N], want) < 1e-5
+    if ld > N:
+        assert torch.isnan(store[:, :, N:]).all()  # nothing written past N
+    out16 = torch.empty(n, M, (N + 7) // 8 * 8, device=cuda_dev, dtype=torch.bfloat16)
+    ops.gemm_batched(a, b, out16[:, :, :N])
+    assert _rel(out16[:, :, :N], want) < 4e-3
