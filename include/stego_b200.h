@@ -221,6 +221,33 @@ STEGO_API int stego_eval_probes(const float* code, const float* code_flip, long 
 STEGO_API int stego_knn_topk(const float* feats, int n, int E, int k, void* planes_scratch, long long* idx_out,
                              float* val_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense CRF post-processing (BASELINE.json configs[4]; src/crf.py:22-45 -> pydensecrf, third-party, parity UNPINNED:
+ * the kernels follow the published densecrf / permutohedral-lattice algorithm as restated by oracle/crf_oracle.py).
+ * Rows of Q / unary / lattice values are 32 floats (classes padded to a warp); C <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+/* Permutohedral embedding of every pixel of an [H][W] frame: features (x/sxy, y/sxy) for d = 2, plus the three
+ * image channels / srgb for d = 5 (image [H][W][3] uint8).  keys [N][d+1] int64 (packed lattice vertex coordinates),
+ * bary [N][d+1] fp32 barycentric weights. */
+STEGO_API int stego_crf_lattice(int H, int W, int d, float sxy, float srgb, const unsigned char* image, long long* keys,
+                                float* bary, void* stream);
+/* Splat scale[pixel] * in[pixel][:C] (in null: ones; scale null: 1) onto the lattice (values: [(M+1)][32], zeroed by the
+ * caller; row 0 = missing neighbour) and blur along the d+1 axes (n1 / n2: [d+1][M] neighbour ids, -1 = missing).
+ * Result in values_tmp for d = 2, in values for d = 5. */
+STEGO_API int stego_crf_splat_blur(int d, long long N, int M, int C, const int* offset, const float* bary, const float* scale,
+                                   const float* in, const int* n1, const int* n2, float* values, float* values_tmp,
+                                   void* stream);
+/* NORMALIZE_SYMMETRIC factor of a kernel from the blurred ones-splat: norm[pixel] = 1 / sqrt(K 1 + 1e-20). */
+STEGO_API int stego_crf_norm(int d, long long N, const int* offset, const float* bary, const float* values, float* norm_out,
+                             void* stream);
+/* Class scores [C][N] at full resolution -> unary energies -log(clip(softmax, 1e-5, 1)) [N][32] and Q_0 = softmax(-U). */
+STEGO_API int stego_crf_unary(const float* logits, float* unary, float* Q, long long N, int C, void* stream);
+/* One mean-field update Q <- softmax(-U + w_g n_g K_g(n_g Q) + w_b n_b K_b(n_b Q)) from the blurred lattice values of the
+ * Gaussian (d = 2) and bilateral (d = 5) kernels; q_out [C][N] and argmax_out [N] are optional (last iteration). */
+STEGO_API int stego_crf_update(const float* unary, const int* off_g, const float* bary_g, const float* val_g, const float* norm_g,
+                               const int* off_b, const float* bary_b, const float* val_b, const float* norm_b, float w_g,
+                               float w_b, float* Q, float* q_out, unsigned char* argmax_out, long long N, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

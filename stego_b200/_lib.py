@@ -33,6 +33,7 @@ _CTYPES = {
     "int*": ctypes.c_void_p,
     "const char*": ctypes.c_char_p,
     "unsigned char*": ctypes.c_void_p,
+    "const unsigned char*": ctypes.c_void_p,
 }
 
 

@@ -183,8 +183,9 @@ def test_gemm_batched_ragged(cuda_dev, n, M, N, K):
     want = torch.einsum("nmk,npk->nmp", a.float(), b.float())
     assert torch.isfinite(store[:, :, :N]).all()
     assert _rel(store[:, :, :N], want) < 1e-5
-    if ld > N:
-        assert torch.isnan(store[:, :, N:]).all()  # nothing written past N
+    if ld > N:  # the row padding up to the 16-byte pitch holds either what was there or zeros, never part of a result
+        pad = store[:, :, N:]
+        assert (torch.isnan(pad) | (pad == 0)).all()
     out16 = torch.empty(n, M, (N + 7) // 8 * 8, device=cuda_dev, dtype=torch.bfloat16)
     ops.gemm_batched(a, b, out16[:, :, :N])
     assert _rel(out16[:, :, :N], want) < 4e-3

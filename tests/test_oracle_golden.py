@@ -130,3 +130,26 @@ def test_knn_oracle_against_brute_force():
     assert (idx[:, 0] == torch.arange(97)).all()
     assert torch.equal(idx, order)
     assert torch.allclose(val, sims.gather(1, order))
+
+
+def test_crf_oracle_lattice_and_mean_field_sanity():
+    """oracle/crf_oracle.py (parity UNPINNED: pydensecrf is absent): the permutohedral filter tracks exact Gaussian filtering
+    (correlation > 0.99 in 2-D, > 0.85 in 5-D: the lattice is an approximation by construction), symmetric normalisation
+    makes K 1 ~ 1-homogeneous, and mean-field on uniform unaries stays uniform."""
+    import numpy as np
+    import crf_oracle as CO
+    rng = np.random.default_rng(0)
+    for d, n, lo in ((2, 500, 0.99), (5, 400, 0.85)):
+        f = (rng.random((d, n)) * 6).astype(np.float32)
+        x = rng.random((n, 3)).astype(np.float32)
+        a = CO.Permutohedral(f).compute(x)
+        b = CO.brute_force_filter(f, x)
+        assert np.corrcoef(a.ravel(), b.ravel())[0, 1] > lo
+    k = CO.DenseKernel(CO.gaussian_features(12, 16, 1.0))
+    U = np.full((12 * 16, 4), -np.log(0.25), np.float32)
+    Q = CO.mean_field(U, [k], [3.0], 5)
+    assert np.abs(Q - 0.25).max() < 1e-5
+    # reverse blur order is the transpose of the filter: <K x, y> == <x, K^T y>
+    lat = CO.Permutohedral((rng.random((3, 200)) * 4).astype(np.float32))
+    x, y = rng.random((200, 1)).astype(np.float32), rng.random((200, 1)).astype(np.float32)
+    assert abs((lat.compute(x) * y).sum() - (x * lat.compute(y, reverse=True)).sum()) < 1e-2 * abs((lat.compute(x) * y).sum())
