@@ -44,9 +44,10 @@ CONFIGS = {
     "c1": dict(model_type="vit_small", res=224, batch=32, desc="ViT-S/8 224x224 batch=32/GPU self+knn+5 random, bf16"),
     "c2": dict(model_type="vit_base", res=320, batch=32, desc="ViT-B/8 320x320 batch=32/GPU, bf16"),
     "c3": dict(model_type="vit_base", res=448, batch=16, desc="ViT-B/8 448x448 batch=16/GPU, bf16"),
-    # BASELINE.json configs[4]: eval probes on 1024x2048 frames (code 128x256); dense-CRF is out of scope (3rd party)
+    # BASELINE.json configs[4]: eval probes + dense CRF on 1024x2048 frames (code 128x256)
     "c4": dict(model_type=None, res=None, batch=4, desc="eval path: upsample + linear probe + ClusterLookup log-probs, "
-                                                        "1024x2048 frames from a 70x128x256 code, fp32"),
+                                                        "1024x2048 frames from a 70x128x256 code, fp32 (value / e2e: the fused "
+                                                        "probe call; eval_pipeline: + flip-TTA, confusion counts, dense CRF)"),
 }
 N_CLASSES = 27
 
@@ -570,6 +571,51 @@ def run_c4(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     run(min(args.warmup, 3), True)
     ms_e2e = run(args.steps, True)
+
+    # the whole eval inner loop of src/eval_segmentation.py:119-141 on the device, once per frame batch: flip-TTA average of
+    # the two codes + upsample + both probes + confusion counts of the raw predictions (ONE fused call), then dense CRF on
+    # the linear and on the cluster log-probabilities (run_crf=True: 2 CRFs per frame), argmax, UnsupervisedMetrics.update
+    def eval_pipeline(nsteps):
+        from stego_b200 import crf as gcrf
+        from stego_b200.eval import UnsupervisedMetrics
+        g2 = torch.Generator().manual_seed(200 + rank)
+        img = torch.randn(B, 3, H, W, generator=g2).to(dev)
+        code2 = torch.randn(B, h, w, C, generator=g2).to(dev).permute(0, 3, 1, 2)
+        label = torch.randint(-1, n, (B, H, W), generator=g2).to(dev)
+        lin_m = UnsupervisedMetrics("final/linear/", n, 0, False, device=dev)
+        clu_m = UnsupervisedMetrics("final/cluster/", n, 0, True, device=dev)
+        raw_lin = torch.zeros(n, n, dtype=torch.int64, device=dev)
+        raw_clu = torch.zeros(n, n, dtype=torch.int64, device=dev)
+        t_crf = 0.0
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(nsteps):
+            lp, cp = fused_probe_log_probs(code, lin, clu, (H, W), 2.0, code_flipped=code2, label=label,
+                                           linear_confusion=raw_lin, cluster_confusion=raw_clu)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            lin_pred = gcrf.batched_crf(None, img, lp).argmax(1)
+            clu_pred = gcrf.batched_crf(None, img, cp).argmax(1)
+            c1.record()
+            lin_m.update(lin_pred, label)
+            clu_m.update(clu_pred, label)
+            c1.synchronize()
+            t_crf += c0.elapsed_time(c1)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        return ms, t_crf, clu_m.compute()
+
+    pipe = None
+    if rank == 0 and not args.no_kernel_rooflines:
+        eval_pipeline(1)
+        pms, pcrf, pmetrics = eval_pipeline(2)
+        pipe = {"frames_per_s": 2 * B / (pms / 1e3), "ms_per_frame": pms / (2 * B), "crf_ms_per_frame_two_crfs": pcrf / (2 * B),
+                "what": "flip-TTA + upsample + linear & cluster probes + confusion counts (one fused call), dense CRF on both "
+                        "probes' log-probabilities (10 mean-field iterations each, permutohedral lattice), argmax, "
+                        "UnsupervisedMetrics.update + Hungarian — synthetic noise frames: worst case for the bilateral lattice",
+                "cluster_metrics_on_noise": pmetrics}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -589,7 +635,8 @@ def run_c4(args, rank, world, local):
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"kernel": "eval_probe_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": by,
-                         "peak_source": peaks["source"]}}
+                         "peak_source": peaks["source"]},
+            **({"eval_pipeline": pipe} if pipe else {})}
     if not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import stego_oracle as O

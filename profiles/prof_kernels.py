@@ -62,5 +62,34 @@ if "ce" in which:
     label = torch.randint(-1, 27, (32, 224, 224), device=dev)
     for _ in range(2):
         linear_probe_ce(code, w, b, label).backward()
+if "ln" in which:
+    x = torch.randn(M, E, device=dev)
+    g = torch.ones(E, device=dev)
+    y = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.layernorm(x, g, g, y)
+if "eval" in which:
+    from stego_b200.eval import fused_probe_log_probs
+    from stego_b200.modules import ClusterLookup
+    code = torch.randn(1, 128, 256, 70, device=dev).permute(0, 3, 1, 2)
+    lin = torch.nn.Conv2d(70, 27, (1, 1)).to(dev)
+    clu = ClusterLookup(70, 27).to(dev)
+    for _ in range(2):
+        fused_probe_log_probs(code, lin, clu, (1024, 2048), 2.0)
+if "knn" in which:
+    from stego_b200.knn import knn_topk
+    feats = torch.randn(20000, 384, device=dev)
+    for _ in range(2):
+        knn_topk(feats, 30)
+if "crf" in which:
+    from stego_b200 import crf
+    img = torch.rand(3, 512, 1024, device=dev)
+    logp = torch.log_softmax(torch.randn(27, 512, 1024, device=dev), 0)
+    crf.mean_field(logp, crf.prepare_image((img - 0.45) / 0.225), 2)
+if "corrdense" in which:
+    f = torch.nn.functional.normalize(torch.randn(32, 1600, 768, device=dev), dim=2).bfloat16()
+    out = torch.empty(32, 1600, 1600, device=dev)
+    for _ in range(2):
+        ops.gemm_batched(f, f, out)
 torch.cuda.synchronize()
 print("done")
