@@ -7,7 +7,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from stego_b200 import ops
+from stego_b200 import _lib, ops
+
+if os.environ.get("STEGO_PROFILE_LIB"):  # a variant build under profiles/_variants (experiments only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["STEGO_PROFILE_LIB"])
 
 dev = torch.device("cuda:0")
 

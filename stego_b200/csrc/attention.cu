@@ -69,6 +69,45 @@ static int g_att_trace_every = 0;
 #define ATT_DIAG(p, bit) false
 #endif
 
+// Round-2 scheduling experiments, kept as compile-time knobs, BOTH OFF in the shipped build because both measured slower
+// (profiles/r2_attention_v3.md; c1 / c2 / c3 in us: shipped 135.1 / 776 / 1330):
+//   ATT_LATE_OWAIT  1: the wait for the previous P V of this warpgroup (P buffer free, O stable) moves from BEFORE the
+//                   exponentials to AFTER them, the packed bf16 P row held in registers meanwhile, to hide the
+//                   tcgen05.mma + commit + mbarrier round trip under the MUFU work: 146.2 / 846 / 1443 (the burst of
+//                   eight 16-byte shared-memory stores behind the wait and the extra spills cost more than the wait).
+//   ATT_POLY        1..4: that many of every four packed pairs take exp2 on the FMA pipe (Cody-Waite split + minimax
+//                   cubic, 7.5e-5 relative error, 50x below the bf16 rounding of P) instead of MUFU.EX2:
+//                   146.5 / 852 / 1449 (1 of 4), 147.8 / 872 / 1508 (2 of 4) — the softmax warps are bound by their
+//                   dependent issue chain, not by the MUFU pipe, so extra FMA-pipe instructions only lengthen it.
+#ifndef ATT_LATE_OWAIT
+#define ATT_LATE_OWAIT 0
+#endif
+#ifndef ATT_POLY
+#define ATT_POLY 0
+#endif
+
+// exp2 of a packed pair on the FMA pipe.  a <= ~2^4 (lazy max), clamped at -125 (2^-125: harmless, no exponent wrap).
+// t = a + 1.5*2^23 holds round(a) in its low mantissa bits; f = a - round(a) in [-0.5, 0.5]; 2^f by a minimax cubic;
+// the integer part is added straight into the exponent field: bits(p) + (bits(t) << 23).
+__device__ __forceinline__ void ex2_poly_x2(uint64_t a2, float& e0, float& e1) {
+  float a0, a1;
+  unpack_f32x2(a2, a0, a1);
+  a0 = fmaxf(a0, -125.f);
+  a1 = fmaxf(a1, -125.f);
+  const uint64_t a = pack_f32x2(a0, a1);
+  const uint64_t t = add_f32x2(a, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t r = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f32x2(r, pack_f32x2(-1.f, -1.f), a);
+  uint64_t q = fma_f32x2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.242611125f, 0.242611125f));
+  q = fma_f32x2(q, f, pack_f32x2(0.693260968f, 0.693260968f));
+  q = fma_f32x2(q, f, pack_f32x2(0.999928057f, 0.999928057f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(q, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 struct AttnParams {
 #ifdef STEGO_ATT_TRACE
   unsigned long long* trace;  // [SLOTS][10 warps][EVENTS][2]
@@ -302,22 +341,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         l_run *= alpha;
       }
       // P V of this warpgroup's previous tile must have retired before P is overwritten or O is touched
-      if (!first) {
-        mbar_wait(&o_full[wg], (it - 1u) & 1u);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, move)) {
+      auto wait_prev_pv = [&]() {
+        if (!first) {
+          mbar_wait(&o_full[wg], (it - 1u) & 1u);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, move)) {
 #pragma unroll 1
-          for (int h = 0; h < ATT_D / 8; ++h) {  // rare path: 8 columns at a time keeps the register budget
-            uint32_t o[8];
-            tmem_ld8(to + h * 8, o);
-            tmem_ld_wait();
+            for (int h = 0; h < ATT_D / 8; ++h) {  // rare path: 8 columns at a time keeps the register budget
+              uint32_t o[8];
+              tmem_ld8(to + h * 8, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
-            tmem_st8(to + h * 8, o);
+              for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+              tmem_st8(to + h * 8, o);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
-      }
+      };
+      if (!ATT_LATE_OWAIT || valid < ATT_BKV) wait_prev_pv();
       const float mc = m_run * c;
       // p = exp2(s*c - m*c), row sum, bf16 P tile into swizzled smem (8 keys = one 16-byte chunk at a time).
       // Full tiles (all but the last) take the select-free path: a per-element mask costs an ISETP + FSEL each.
@@ -332,19 +374,37 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint32_t wv[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const uint64_t s2 = pack_f32x2(__uint_as_float(v[h][8 * g + 2 * t]), __uint_as_float(v[h][8 * g + 2 * t + 1]));
-              float a0, a1;
-              unpack_f32x2(fma_f32x2(s2, c2, nmc2), a0, a1);
-              const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-              wv[t] = pack_bf16x2(e0, e1);
+              const uint64_t a2 = fma_f32x2(s2, c2, nmc2);
+              float e0, e1;
+              if (t < ATT_POLY) {
+                ex2_poly_x2(a2, e0, e1);
+              } else {
+                float a0, a1;
+                unpack_f32x2(a2, a0, a1);
+                e0 = ex2_approx(a0);
+                e1 = ex2_approx(a1);
+              }
+              // the packed bf16 pair replaces the first of the two score registers it came from (no second array)
+              v[h][8 * g + 2 * t] = pack_bf16x2(e0, e1);
               if (t & 1) rs2b = add_f32x2(rs2b, pack_f32x2(e0, e1));
               else rs2a = add_f32x2(rs2a, pack_f32x2(e0, e1));
             }
-            *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(h * 4 + g) << 4) ^ rx)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            if (!ATT_LATE_OWAIT)
+              *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(h * 4 + g) << 4) ^ rx)) =
+                  make_uint4(v[h][8 * g], v[h][8 * g + 2], v[h][8 * g + 4], v[h][8 * g + 6]);
           }
+        }
+        if (ATT_LATE_OWAIT) {
+          wait_prev_pv();
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(h * 4 + g) << 4) ^ rx)) =
+                  make_uint4(v[h][8 * g], v[h][8 * g + 2], v[h][8 * g + 4], v[h][8 * g + 6]);
         }
         float s0, s1;
         unpack_f32x2(add_f32x2(rs2a, rs2b), s0, s1);

@@ -290,6 +290,181 @@ eval_probe_kernel(EvalProbeParams p) {
   }
 }
 
+
+// ---- four pixels per thread (round 2) --------------------------------------------------------------------------------
+// The pixel-per-thread kernel above is issue-bound, not HBM-bound (ncu: 70 % issue-active, 2900 warp instructions per
+// 32 pixels, 20 % of the DRAM throughput): every class costs four scalar shared-memory loads, four FMAs and a strided
+// 4-byte store per pixel.  When the horizontal upsampling factor is a multiple of 8, four x-adjacent output pixels
+// (X = 4t .. 4t+3) always interpolate between the same two low-res columns, so a thread that owns all four
+//   * loads the four corner rows once, as float4 (LDS.128, same address across most of the warp = broadcast),
+//   * interpolates vertically once:  L[k] = a + ly (c - a),  R[k] = b + ly (d - b),  D[k] = R[k] - L[k],
+//   * evaluates each pixel as z_j[k] = L[k] + lx_j D[k]  (one FMA per class), recomputing it in the three passes
+//     (max/argmax, sum of exponentials, output) instead of keeping 4 x 27 logits in registers,
+//   * writes one float4 per class plane (a warp covers 512 contiguous bytes of a plane row).
+// Class counts are template parameters (27/27 = both shipped label sets); any other shape takes the generic kernel.
+constexpr int EV4_TW = 64, EV4_ROWS = 4, EV4_W = 4 * EV4_TW;  // CTA tile: 256 x 4 pixels, 256 threads
+
+template <int N, bool SCALED>
+__device__ __forceinline__ void ev4_probe(const float* ea, const float* eb, const float* ec, const float* ed, float ly,
+                                          const float (&lx)[4], const float (&scale)[4], float* out, long long plane,
+                                          int (&pred)[4]) {
+  constexpr int Q = (N + 3) / 4;
+  float L[4 * Q], D[4 * Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const float4 a = reinterpret_cast<const float4*>(ea)[q], b = reinterpret_cast<const float4*>(eb)[q];
+    const float4 c = reinterpret_cast<const float4*>(ec)[q], d = reinterpret_cast<const float4*>(ed)[q];
+    const float l0 = fmaf(ly, c.x - a.x, a.x), l1 = fmaf(ly, c.y - a.y, a.y), l2 = fmaf(ly, c.z - a.z, a.z),
+                l3 = fmaf(ly, c.w - a.w, a.w);
+    L[4 * q] = l0; L[4 * q + 1] = l1; L[4 * q + 2] = l2; L[4 * q + 3] = l3;
+    D[4 * q] = fmaf(ly, d.x - b.x, b.x) - l0;
+    D[4 * q + 1] = fmaf(ly, d.y - b.y, b.y) - l1;
+    D[4 * q + 2] = fmaf(ly, d.z - b.z, b.z) - l2;
+    D[4 * q + 3] = fmaf(ly, d.w - b.w, b.w) - l3;
+  }
+  float lse[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mx = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float z = fmaf(lx[j], D[k], L[k]);
+      if (SCALED) z *= scale[j];
+      if (z > mx) { mx = z; arg = k; }
+    }
+    pred[j] = arg;
+    float se = 0.f;
+    if (out) {
+      const float nmx = -mx * 1.4426950408889634f;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float z = fmaf(lx[j], D[k], L[k]);
+        if (SCALED) z *= scale[j];
+        se += ex2_approx(fmaf(z, 1.4426950408889634f, nmx));
+      }
+    }
+    lse[j] = mx + __logf(se);
+  }
+  if (out) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float4 o;
+      o.x = fmaf(lx[0], D[k], L[k]); o.y = fmaf(lx[1], D[k], L[k]); o.z = fmaf(lx[2], D[k], L[k]); o.w = fmaf(lx[3], D[k], L[k]);
+      if (SCALED) { o.x *= scale[0]; o.y *= scale[1]; o.z *= scale[2]; o.w *= scale[3]; }
+      o.x -= lse[0]; o.y -= lse[1]; o.z -= lse[2]; o.w -= lse[3];
+      *reinterpret_cast<float4*>(out + k * plane) = o;
+    }
+  }
+}
+
+template <int NL, int NC>
+__global__ void __launch_bounds__(EV4_TW* EV4_ROWS, 2)
+eval_probe_vec4_kernel(EvalProbeParams p) {
+  extern __shared__ __align__(16) float slr[];  // [box_h*box_w][EV_LD]
+  __shared__ unsigned int hist[2][32 * 32];     // [probe][pred * 32 + actual]
+  const bool want_conf = p.label != nullptr;
+  if (want_conf)
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) (&hist[0][0])[i] = 0u;
+  const int tiles_x = (p.W + EV4_W - 1) / EV4_W, tiles_y = (p.H + EV4_ROWS - 1) / EV4_ROWS;
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int X0 = tx * EV4_W, Y0 = ty * EV4_ROWS;
+  const int Xl = min(X0 + EV4_W - 1, p.W - 1), Yl = min(Y0 + EV4_ROWS - 1, p.H - 1);
+  const float sy = static_cast<float>(p.h) / p.H, sx = static_cast<float>(p.w) / p.W;
+  int by0, by1, bx0, bx1, tmp;
+  float ftmp;
+  ev_src_index(Y0, sy, p.h, by0, tmp, ftmp);
+  ev_src_index(Yl, sy, p.h, tmp, by1, ftmp);
+  ev_src_index(X0, sx, p.w, bx0, tmp, ftmp);
+  ev_src_index(Xl, sx, p.w, tmp, bx1, ftmp);
+  const int bh = by1 - by0 + 1, bw = bx1 - bx0 + 1;
+  const long long base = 1ll * b * p.h * p.w;
+  {
+    constexpr int LD4 = EV_LD / 4;
+    float4* s4 = reinterpret_cast<float4*>(slr);
+    const float4* g4 = reinterpret_cast<const float4*>(p.lr);
+    for (int i = threadIdx.x; i < bh * bw * LD4; i += blockDim.x) {
+      const int cell = i / LD4, k = i % LD4;
+      const int r = cell / bw, c = cell % bw;
+      s4[i] = g4[(base + 1ll * (by0 + r) * p.w + bx0 + c) * LD4 + k];
+    }
+  }
+  __syncthreads();
+  const int X = X0 + 4 * (threadIdx.x % EV4_TW), Y = Y0 + threadIdx.x / EV4_TW;
+  const bool active = X < p.W && Y < p.H;  // W % 4 == 0: a group is entirely inside or outside
+  if (active) {
+    int y0, y1, x0, x1;
+    float ly, lx[4];
+    ev_src_index(Y, sy, p.h, y0, y1, ly);
+    ev_src_index(X, sx, p.w, x0, x1, lx[0]);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {  // same two columns for the whole group (host checks the upsampling factor)
+      int t0, t1;
+      ev_src_index(X + j, sx, p.w, t0, t1, lx[j]);
+    }
+    y0 -= by0; y1 -= by0; x0 -= bx0; x1 -= bx0;
+    const float* ea = slr + (y0 * bw + x0) * EV_LD;
+    const float* eb = slr + (y0 * bw + x1) * EV_LD;
+    const float* ec = slr + (y1 * bw + x0) * EV_LD;
+    const float* ed = slr + (y1 * bw + x1) * EV_LD;
+    const long long plane = 1ll * p.H * p.W;
+    const long long pix = 1ll * Y * p.W + X;
+    int lin_pred[4] = {-1, -1, -1, -1}, clu_pred[4] = {-1, -1, -1, -1};
+    float one[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p.lin_logp || p.lin_arg) {
+      ev4_probe<NL, false>(ea, eb, ec, ed, ly, lx, one, p.lin_logp ? p.lin_logp + (1ll * b * NL) * plane + pix : nullptr,
+                           plane, lin_pred);
+      if (p.lin_arg)
+        *reinterpret_cast<uchar4*>(p.lin_arg + b * plane + pix) =
+            make_uchar4((unsigned char)lin_pred[0], (unsigned char)lin_pred[1], (unsigned char)lin_pred[2], (unsigned char)lin_pred[3]);
+    }
+    if (p.clu_logp || p.clu_arg) {
+      const float gaa = ea[EV_SS], gbb = eb[EV_SS], gcc = ec[EV_SS], gdd = ed[EV_SS];
+      const float gab = ev_gram(slr, bw, y0, x0, y0, x1), gac = ev_gram(slr, bw, y0, x0, y1, x0);
+      const float gad = ev_gram(slr, bw, y0, x0, y1, x1), gbc = ev_gram(slr, bw, y0, x1, y1, x0);
+      const float gbd = ev_gram(slr, bw, y0, x1, y1, x1), gcd = ev_gram(slr, bw, y1, x0, y1, x1);
+      float scale[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wa = (1.f - ly) * (1.f - lx[j]), wb = (1.f - ly) * lx[j], wc = ly * (1.f - lx[j]), wd = ly * lx[j];
+        float n2 = wa * wa * gaa + wb * wb * gbb + wc * wc * gcc + wd * wd * gdd;
+        n2 += 2.f * (wa * wb * gab + wa * wc * gac + wa * wd * gad + wb * wc * gbc + wb * wd * gbd + wc * wd * gcd);
+        scale[j] = p.alpha / fmaxf(sqrtf(fmaxf(n2, 0.f)), 1e-12f);
+      }
+      ev4_probe<NC, true>(ea + 32, eb + 32, ec + 32, ed + 32, ly, lx, scale,
+                          p.clu_logp ? p.clu_logp + (1ll * b * NC) * plane + pix : nullptr, plane, clu_pred);
+      if (p.clu_arg)
+        *reinterpret_cast<uchar4*>(p.clu_arg + b * plane + pix) =
+            make_uchar4((unsigned char)clu_pred[0], (unsigned char)clu_pred[1], (unsigned char)clu_pred[2], (unsigned char)clu_pred[3]);
+    }
+    if (want_conf) {  // UnsupervisedMetrics.update (src/utils.py:219-229)
+      const long long li = 1ll * b * plane + pix;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        long long lab;
+        if (p.label_bytes == 8) lab = reinterpret_cast<const long long*>(p.label)[li + j];
+        else if (p.label_bytes == 4) lab = reinterpret_cast<const int*>(p.label)[li + j];
+        else lab = reinterpret_cast<const unsigned char*>(p.label)[li + j];
+        if (lab >= 0 && lab < p.n_cls) {
+          if (lin_pred[j] >= 0 && lin_pred[j] < p.n_cls) atomicAdd(&hist[0][lin_pred[j] * 32 + static_cast<int>(lab)], 1u);
+          if (clu_pred[j] >= 0 && clu_pred[j] < p.n_cls) atomicAdd(&hist[1][clu_pred[j] * 32 + static_cast<int>(lab)], 1u);
+        }
+      }
+    }
+  }
+  if (want_conf) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) {
+      const unsigned int cnt = (&hist[0][0])[i];
+      if (cnt == 0u) continue;
+      const int probe = i >> 10, pred = (i >> 5) & 31, act = i & 31;
+      unsigned long long* dst = probe ? p.clu_conf : p.lin_conf;
+      if (dst && act < p.n_cls && pred < (probe ? NC : NL)) atomicAdd(dst + pred * p.n_cls + act, (unsigned long long)cnt);
+    }
+  }
+}
+
 }  // namespace stego
 
 using namespace stego;
@@ -325,20 +500,40 @@ extern "C" int stego_eval_probes(const float* code, const float* code_flip, long
   p.label = label; p.label_bytes = label_bytes; p.n_cls = n_label_classes;
   p.lin_conf = reinterpret_cast<unsigned long long*>(lin_confusion);
   p.clu_conf = reinterpret_cast<unsigned long long*>(clu_confusion);
-  p.box_h = (int)((double)EVT_H * h / H) + 3;
-  p.box_w = (int)((double)EVT_W * w / W) + 3;
+  // four pixels per thread when a group of four x-adjacent pixels always shares its two source columns: integer
+  // horizontal factor that is a multiple of 8 (every patch-8 / patch-16 model evaluated at the label resolution)
+  const bool vec4 = n_lin == 27 && n_clu == 27 && W % w == 0 && (W / w) % 8 == 0 &&
+                    (!lin_log_probs || (reinterpret_cast<uintptr_t>(lin_log_probs) & 15) == 0) &&
+                    (!clu_log_probs || (reinterpret_cast<uintptr_t>(clu_log_probs) & 15) == 0) &&
+                    (!lin_argmax || (reinterpret_cast<uintptr_t>(lin_argmax) & 3) == 0) &&
+                    (!clu_argmax || (reinterpret_cast<uintptr_t>(clu_argmax) & 3) == 0) &&
+                    (reinterpret_cast<uintptr_t>(lr_scratch) & 15) == 0;
+  const int tile_h = vec4 ? EV4_ROWS : EVT_H, tile_w = vec4 ? EV4_W : EVT_W;
+  p.box_h = (int)((double)tile_h * h / H) + 3;
+  p.box_w = (int)((double)tile_w * w / W) + 3;
   if (p.box_h > h) p.box_h = h;
   if (p.box_w > w) p.box_w = w;
   const size_t smem = (size_t)p.box_h * p.box_w * EV_LD * sizeof(float);
   STEGO_CHECK_ARG(smem <= 200 * 1024, "stego_eval_probes: upsample ratio needs %zu B of shared memory", smem);
+  const long long tiles = 1ll * B * ((H + tile_h - 1) / tile_h) * ((W + tile_w - 1) / tile_w);
+  STEGO_CHECK_ARG(tiles < (1ll << 31), "stego_eval_probes: too many tiles");
+  if (vec4) {
+    static size_t conf4 = 0;
+    if (smem > 48 * 1024 && smem > conf4) {
+      cudaError_t e = cudaFuncSetAttribute(eval_probe_vec4_kernel<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(eval_probe_vec4)");
+      conf4 = smem;
+    }
+    eval_probe_vec4_kernel<27, 27><<<(unsigned)tiles, EV4_TW * EV4_ROWS, smem, stream>>>(p);
+    STEGO_CHECK_LAUNCH("eval_probe_vec4_kernel");
+    return STEGO_OK;
+  }
   static size_t conf = 0;
   if (smem > 48 * 1024 && smem > conf) {
     cudaError_t e = cudaFuncSetAttribute(eval_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(eval_probe)");
     conf = smem;
   }
-  const long long tiles = 1ll * B * ((H + EVT_H - 1) / EVT_H) * ((W + EVT_W - 1) / EVT_W);
-  STEGO_CHECK_ARG(tiles < (1ll << 31), "stego_eval_probes: too many tiles");
   eval_probe_kernel<<<(unsigned)tiles, EVT_W * EVT_ROWS, smem, stream>>>(p);
   STEGO_CHECK_LAUNCH("eval_probe_kernel");
   return STEGO_OK;
