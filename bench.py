@@ -400,6 +400,15 @@ def kernel_rooflines(cfgd, peaks, dev):
     fl = 2.0 * 2 * B2 * N * N * E
     out["attention"] = dict(ms=ms, tflops=fl / ms / 1e9, gbs=(M * 4 * E * 2) / ms / 1e6, flops=fl, bytes=M * 4 * E * 2,
                             launches_per_step=12)
+    # head-dim-64 attention needs one exponential per 256 tensor flops; MUFU.EX2 issues 16 / clk / SM, so the exponentials
+    # alone cap the kernel at half the bf16 tensor peak (profiles/r2_attention_v3.md).  Tile-padded count: 128-row query
+    # tiles x 64-key tiles, what the kernel actually evaluates.
+    n_exp = float(B2 * heads) * (-(-N // 128) * 128) * (-(-N // 64) * 64)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    out["attention"]["exp_per_launch"] = n_exp
+    out["attention"]["exp_per_clk_per_sm_needed_at_peak"] = 16.0
+    out["attention"]["exp_rate_gexp_s"] = n_exp / ms / 1e6
+    out["attention"]["sm_count"] = sm_count
     xr = rnd(M, E)
     gam, bet = rnd(E), rnd(E)
     ms = time_kernel(lambda: ops.layernorm(xr, gam, bet, x_bf), flush=flush)
@@ -633,7 +642,7 @@ def run_c4(args, rank, world, local):
             "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": B * h * w * C * 4,
                     "d2h_bytes_per_step": 2 * B * H * W, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "eval_probe_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+            "roofline": {"kernel": "eval_probe_vec4_kernel (+ eval_prep_kernel, both inside the timed call)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": by,
                          "peak_source": peaks["source"]},
             **({"eval_pipeline": pipe} if pipe else {})}
@@ -900,6 +909,13 @@ def main():
                             "algorithmic_bytes_per_launch": d["bytes"],
                             "algorithmic_flops_per_launch": d["flops"], "ms_per_launch": d["ms"],
                             "share_of_step": d["share_of_step"], "peak_source": peaks["source"] + ", burst"}
+        if dom == "attention" and clocks.get("sm_mhz"):
+            # second ceiling of this kernel: the MUFU pipe (16 ex2 / clk / SM at the clock sampled during the run)
+            mufu_peak = 16.0 * d["sm_count"] * clocks["sm_mhz"] * 1e6 / 1e9  # Gexp/s
+            line["roofline"]["mufu"] = {"exp_per_launch": d["exp_per_launch"], "achieved_gexp_s": d["exp_rate_gexp_s"],
+                                        "peak_gexp_s": mufu_peak, "frac": d["exp_rate_gexp_s"] / mufu_peak,
+                                        "note": "head_dim 64: 256 tensor flop per exponential, so the MUFU pipe caps this kernel at "
+                                                "0.5 of the bf16 tensor peak; frac here = share of that second ceiling"}
         c = ks["corr_loss_fwd"]
         line["corr_roofline"] = {"kernel": "corr_loss_fwd (fd+cd einsums + loss reduction, 7 calls x B images)",
                                  "ms_per_launch": c["ms"], "achieved_tflops": c["tflops"],

@@ -248,6 +248,34 @@ STEGO_API int stego_crf_update(const float* unary, const int* off_g, const float
                                const int* off_b, const float* bary_b, const float* val_b, const float* norm_b, float w_g,
                                float w_b, float* Q, float* q_out, unsigned char* argmax_out, long long N, int C, void* stream);
 
+/* ---- contrastive CRF loss (optional training term; replaces ContrastiveCRFLoss.forward, src/modules.py:449-469, and its
+ * autograd backward).  guidance [B, Cg <= 3, H, W] and clusters [B, C <= 80, H, W] are fp32 with arbitrary element strides;
+ * coords is the reference's int64 [2][n] tensor (row 0 indexes H, row 1 indexes W; shared by the batch).
+ * Workspace, caller-allocated, NP = round_up(n, 64): sel [B][C][NP] floats, gsel [B][NP][4] floats, pos [NP][2] ints.
+ * out [B][n][n] = -(<sel_a, sel_b> * (w1 exp(-|dp|^2/2alpha - |dI|^2/2beta) + w2 exp(-|dp|^2/2gamma) - shift)). */
+STEGO_API int stego_crf_loss_fwd(const float* guidance, long long g_sb, long long g_sc, long long g_sy, long long g_sx, int Cg,
+                                 const float* clusters, long long c_sb, long long c_sc, long long c_sy, long long c_sx, int C,
+                                 const long long* coords, int B, int n, int H, int W, float alpha, float beta, float gamma,
+                                 float w1, float w2, float shift, float* sel, float* gsel, int* pos, float* out, void* stream);
+/* Backward over the workspace the forward filled: grad_out [B][n][n] contiguous, dsel [B][C][NP] scratch; the gradient is
+ * ACCUMULATED into dclusters (element strides given; zero-fill it first) with atomics (coords may repeat). */
+STEGO_API int stego_crf_loss_bwd(const float* grad_out, const float* sel, const float* gsel, const int* pos,
+                                 const long long* coords, int B, int C, int n, float alpha, float beta, float gamma, float w1,
+                                 float w2, float shift, float* dsel, float* dclusters, long long c_sb, long long c_sc,
+                                 long long c_sy, long long c_sx, void* stream);
+
+/* ---- per-pixel cosine similarity <normalize(a), normalize(b)> over the channel axis and its backward: the arithmetic of the
+ * optional reconstruction and augmentation-alignment terms (src/train_segmentation.py:183-199; F.normalize eps semantics of
+ * src/modules.py:275-276).  a, b: fp32 [B, C, H, W] with arbitrary element strides; cosv / inva / invb: [B*H*W] floats. */
+STEGO_API int stego_cosine_fwd(const float* a, long long a_sb, long long a_sc, long long a_sy, long long a_sx, const float* b,
+                               long long b_sb, long long b_sc, long long b_sy, long long b_sx, int B, int C, int H, int W,
+                               float eps, float* cosv, float* inva, float* invb, void* stream);
+/* grad_cos [B*H*W]; da / db (either may be null) are written with the strides of a / b. */
+STEGO_API int stego_cosine_bwd(const float* a, long long a_sb, long long a_sc, long long a_sy, long long a_sx, const float* b,
+                               long long b_sb, long long b_sc, long long b_sy, long long b_sx, int B, int C, int H, int W,
+                               float eps, const float* cosv, const float* inva, const float* invb, const float* grad_cos,
+                               float* da, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

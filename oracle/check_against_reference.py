@@ -127,6 +127,22 @@ def run_checks() -> bool:
     ok &= _close(got_code, want_code.detach(), 1e-5, "head code (dropout masks replayed)")
     ok &= _close(got_feat, want_feat, 1e-6, "head returned feats")
 
+    # ---- ContrastiveCRFLoss (modules.py:437-469), train_config.yml:131-137 parameters; coords replayed from the seed
+    crf = ref.ContrastiveCRFLoss(200, .5, .15, .05, 10.0, 3.0, 0.00)
+    torch.manual_seed(31)
+    gd = torch.rand(2, 3, 20, 24)
+    cl_ = torch.nn.functional.normalize(torch.randn(2, 70, 20, 24), dim=1).requires_grad_(True)
+    torch.manual_seed(32)
+    want = crf(gd, cl_)
+    gw, = torch.autograd.grad(want.mean(), cl_)
+    torch.manual_seed(32)
+    coords = torch.cat([torch.randint(0, 20, size=[1, 200]), torch.randint(0, 24, size=[1, 200])], 0)
+    c2_ = cl_.detach().clone().requires_grad_(True)
+    got = O.contrastive_crf_loss(gd, c2_, coords, .5, .15, .05, 10.0, 3.0, 0.00)
+    gg, = torch.autograd.grad(got.mean(), c2_)
+    ok &= _close(got.detach(), want.detach(), 1e-6, "ContrastiveCRFLoss")
+    ok &= _close(gg, gw, 1e-6, "ContrastiveCRFLoss d/dclusters")
+
     print("ORACLE PINNED AGAINST REFERENCE" if ok else "ORACLE MISMATCH")
     return bool(ok)
 

@@ -119,6 +119,20 @@ def main():
         rows.append(torch.stack([ref.super_perm(size, torch.device("cpu")) for _ in range(3)]))
     torch.save(dict(recipe="for size in (1,2,5,16,32): manual_seed(1000+size); 3 x super_perm(size)",
                     draws=rows), os.path.join(OUT, "super_perm.pt"))
+    # ---- 6. ContrastiveCRFLoss (modules.py:437-469) at the training call's shapes (56 x 56, 70 channels), 300 samples
+    torch.manual_seed(51)
+    gd = torch.rand(2, 3, 56, 56) * 4 - 2
+    cl = torch.nn.functional.normalize(torch.randn(2, 70, 56, 56), dim=1).requires_grad_(True)
+    crf = ref.ContrastiveCRFLoss(300, .5, .15, .05, 10.0, 3.0, 0.00)
+    torch.manual_seed(52)
+    out = crf(gd, cl)
+    g, = torch.autograd.grad(out.mean(), cl)
+    torch.save(dict(recipe="manual_seed(51); guidance = rand(2,3,56,56)*4-2; clusters = normalize(randn(2,70,56,56), dim=1); "
+                           "ContrastiveCRFLoss(300, .5, .15, .05, 10, 3, 0) under manual_seed(52) (coords = randint(56,[1,300]) x 2); "
+                           "grad of out.mean()",
+                    out_sub=out.detach().reshape(-1)[::97].clone(), out_mean=out.detach().mean(), out_abs_sum=out.detach().abs().sum(),
+                    grad_sub=g.reshape(-1)[::53].clone(), grad_abs_sum=g.abs().sum()),
+               os.path.join(OUT, "contrastive_crf_loss.pt"))
     for f_ in sorted(os.listdir(OUT)):
         print(f_, os.path.getsize(os.path.join(OUT, f_)))
 

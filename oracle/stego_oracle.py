@@ -179,6 +179,21 @@ def cluster_lookup(x: Tensor, clusters: Tensor, alpha: Optional[float], log_prob
 # --------------------------------------------------------------------------------------------------
 # src/dino/vision_transformer.py — frozen DINO ViT forward (functional, reference state-dict names)
 # --------------------------------------------------------------------------------------------------
+def contrastive_crf_loss(guidance: Tensor, clusters: Tensor, coords: Tensor, alpha: float, beta: float, gamma: float,
+                         w1: float, w2: float, shift: float) -> Tensor:
+    """ContrastiveCRFLoss.forward (src/modules.py:449-469) with the coordinate draw (`:456-458`, two torch.randint calls: row
+    indices then column indices, shared by the batch) made an argument.  guidance [B, Cg, H, W], clusters [B, C, H, W],
+    coords int64 [2, n] -> [B, n, n]."""
+    ys, xs = coords[0], coords[1]
+    g = guidance[:, :, ys, xs]  # [B, Cg, n]
+    c = clusters[:, :, ys, xs]  # [B, C, n]
+    dpos = ((ys[:, None] - ys[None, :]) ** 2 + (xs[:, None] - xs[None, :]) ** 2)[None]  # int64, like the reference
+    dgui = (g[:, :, :, None] - g[:, :, None, :]).square().sum(1)
+    kernel = w1 * torch.exp(-dpos / (2 * alpha) - dgui / (2 * beta)) + w2 * torch.exp(-dpos / (2 * gamma)) - shift
+    gram = torch.einsum("bka,bkc->bac", c, c)
+    return -(gram * kernel)
+
+
 def vit_config(arch: str) -> Dict[str, int]:
     """vision_transformer.py:266-277 (vit_small / vit_base); depth 12, mlp_ratio 4, LN eps 1e-6."""
     if arch == "vit_small":

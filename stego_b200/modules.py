@@ -589,8 +589,90 @@ class NetWithActivations(torch.nn.Module):
         return activations
 
 
+class _PixelCosineFn(torch.autograd.Function):
+    """cos[b, y, x] = <normalize(a)[b, :, y, x], normalize(b)[b, :, y, x]> (F.normalize eps 1e-10, modules.py:275-276): one
+    read of each operand in the forward, one in the backward (csrc/cosine_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _lib.require_cuda(a, b)
+        lib = _lib.load()
+        a32, b32 = a.detach().float(), b.detach().float()
+        B, C, H, W = a32.shape
+        assert b32.shape == a32.shape
+        cosv = torch.empty(B, H, W, dtype=torch.float32, device=a.device)
+        inva, invb = torch.empty_like(cosv), torch.empty_like(cosv)
+        _lib.check(lib.stego_cosine_fwd(_lib.ptr(a32), *a32.stride(), _lib.ptr(b32), *b32.stride(), B, C, H, W, 1e-10,
+                                        _lib.ptr(cosv), _lib.ptr(inva), _lib.ptr(invb), _lib.stream()), "stego_cosine_fwd")
+        ctx.save_for_backward(a32, b32, cosv, inva, invb)
+        return cosv
+
+    @staticmethod
+    def backward(ctx, g):
+        a32, b32, cosv, inva, invb = ctx.saved_tensors
+        lib = _lib.load()
+        B, C, H, W = a32.shape
+        need_a, need_b = ctx.needs_input_grad
+        da = torch.empty_strided(a32.shape, a32.stride(), dtype=torch.float32, device=a32.device) if need_a else None
+        db = torch.empty_strided(b32.shape, b32.stride(), dtype=torch.float32, device=b32.device) if need_b else None
+        if not (need_a or need_b):
+            return None, None
+        _lib.check(lib.stego_cosine_bwd(_lib.ptr(a32), *a32.stride(), _lib.ptr(b32), *b32.stride(), B, C, H, W, 1e-10,
+                                        _lib.ptr(cosv), _lib.ptr(inva), _lib.ptr(invb), _lib.ptr(g.float().contiguous()),
+                                        _lib.ptr(da), _lib.ptr(db), _lib.stream()), "stego_cosine_bwd")
+        return da, db
+
+
+def pixel_cosine(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """`(norm(a) * norm(b)).sum(1)` of the reference's optional alignment terms (train_segmentation.py:185,194-198) -> [B, h, w]."""
+    return _PixelCosineFn.apply(a, b)
+
+
+class _CrfLossFn(torch.autograd.Function):
+    """Fused pairwise-kernel x Gram product of ContrastiveCRFLoss (csrc/crf_loss.cu); gradient w.r.t. `clusters` only
+    (the reference's guidance is the resized input image: no gradient ever flows into it)."""
+
+    @staticmethod
+    def forward(ctx, guidance, clusters, coords, alpha, beta, gamma, w1, w2, shift):
+        _lib.require_cuda(guidance, clusters, coords)
+        lib = _lib.load()
+        B, C, H, W = clusters.shape
+        n = coords.shape[1]
+        NP = _round_up(n, 64)
+        g = guidance.detach().float()
+        c = clusters.detach().float()
+        coords = coords.contiguous()
+        dev = c.device
+        sel = torch.empty(B, C, NP, dtype=torch.float32, device=dev)
+        gsel = torch.empty(B, NP, 4, dtype=torch.float32, device=dev)
+        pos = torch.empty(NP, 2, dtype=torch.int32, device=dev)
+        out = torch.empty(B, n, n, dtype=torch.float32, device=dev)
+        _lib.check(lib.stego_crf_loss_fwd(_lib.ptr(g), *g.stride(), g.shape[1], _lib.ptr(c), *c.stride(), C, _lib.ptr(coords),
+                                          B, n, H, W, float(alpha), float(beta), float(gamma), float(w1), float(w2),
+                                          float(shift), _lib.ptr(sel), _lib.ptr(gsel), _lib.ptr(pos), _lib.ptr(out),
+                                          _lib.stream()), "stego_crf_loss_fwd")
+        ctx.save_for_backward(sel, gsel, pos, coords)
+        ctx.meta = (B, C, H, W, n, float(alpha), float(beta), float(gamma), float(w1), float(w2), float(shift))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sel, gsel, pos, coords = ctx.saved_tensors
+        B, C, H, W, n, alpha, beta, gamma, w1, w2, shift = ctx.meta
+        lib = _lib.load()
+        go = grad_out.float().contiguous()
+        dsel = torch.empty_like(sel)
+        dclusters = torch.zeros(B, C, H, W, dtype=torch.float32, device=sel.device)
+        _lib.check(lib.stego_crf_loss_bwd(_lib.ptr(go), _lib.ptr(sel), _lib.ptr(gsel), _lib.ptr(pos), _lib.ptr(coords), B, C, n,
+                                          alpha, beta, gamma, w1, w2, shift, _lib.ptr(dsel), _lib.ptr(dclusters),
+                                          *dclusters.stride(), _lib.stream()), "stego_crf_loss_bwd")
+        return None, dclusters, None, None, None, None, None, None, None
+
+
 class ContrastiveCRFLoss(nn.Module):
-    """modules.py:437-469 (crf_weight is 0 in the shipped config; plain torch)."""
+    """modules.py:437-469: same constructor, same two `torch.randint` draws (row indices, then column indices) in the same
+    order on the same device, same [B, n_samples, n_samples] result; the pairwise kernel, the Gram matrix of the selected
+    code vectors and their product are one fused kernel (and one for the backward) instead of eight [B, n, n] temporaries."""
 
     def __init__(self, n_samples, alpha, beta, gamma, w1, w2, shift):
         super().__init__()
@@ -599,18 +681,17 @@ class ContrastiveCRFLoss(nn.Module):
         self.n_samples = n_samples
         self.shift = shift
 
+    def draw_coords(self, h: int, w: int, device) -> torch.Tensor:
+        return torch.cat([torch.randint(0, h, size=[1, self.n_samples], device=device),
+                          torch.randint(0, w, size=[1, self.n_samples], device=device)], 0)
+
+    def forward_with_coords(self, guidance, clusters, coords):
+        return _CrfLossFn.apply(guidance, clusters, coords, self.alpha, self.beta, self.gamma, self.w1, self.w2, self.shift)
+
     def forward(self, guidance, clusters):
-        device = clusters.device
+        if not clusters.is_cuda:
+            raise RuntimeError("stego_b200.ContrastiveCRFLoss: CUDA tensors required (no CPU fallback)")
         assert guidance.shape[0] == clusters.shape[0]
         assert guidance.shape[2:] == clusters.shape[2:]
-        h, w = guidance.shape[2], guidance.shape[3]
-        coords = torch.cat([torch.randint(0, h, size=[1, self.n_samples], device=device),
-                            torch.randint(0, w, size=[1, self.n_samples], device=device)], 0)
-        sel_g = guidance[:, :, coords[0, :], coords[1, :]]
-        coord_diff = (coords.unsqueeze(-1) - coords.unsqueeze(1)).square().sum(0).unsqueeze(0)
-        guidance_diff = (sel_g.unsqueeze(-1) - sel_g.unsqueeze(2)).square().sum(1)
-        sim_kernel = self.w1 * torch.exp(- coord_diff / (2 * self.alpha) - guidance_diff / (2 * self.beta)) + \
-            self.w2 * torch.exp(- coord_diff / (2 * self.gamma)) - self.shift
-        sel_c = clusters[:, :, coords[0, :], coords[1, :]]
-        cluster_sims = torch.einsum("nka,nkb->nab", sel_c, sel_c)
-        return -(cluster_sims * sim_kernel)
+        coords = self.draw_coords(guidance.shape[2], guidance.shape[3], clusters.device)
+        return self.forward_with_coords(guidance, clusters, coords)

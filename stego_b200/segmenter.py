@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from . import _lib, corr
 from .modules import ClusterLookup, ContrastiveCorrelationLoss, ContrastiveCRFLoss, DinoFeaturizer, \
-    FeaturePyramidNet, _ClusterLookupFn, norm, sample
+    FeaturePyramidNet, _ClusterLookupFn, norm, pixel_cosine, sample
 
 
 # --------------------------------------------------------------------------------------------------
@@ -393,18 +393,19 @@ class LitUnsupervisedSegmenter(nn.Module):
             loss = loss + (cfg.pos_inter_weight * pos_inter_loss + cfg.pos_intra_weight * pos_intra_loss +
                            cfg.neg_inter_weight * neg_inter_loss) * cfg.correspondence_weight
 
-        # optional terms, off in the shipped config (train_config.yml: rec/aug_alignment/crf weights 0): plain torch
+        # optional terms, off in the shipped config (train_config.yml: rec/aug_alignment/crf weights 0): fused kernels for the
+        # pairwise CRF term and the two cosine alignments; resize / grid_sample / the decoder conv stay torch ops
         if cfg.rec_weight > 0 or cfg.aug_alignment_weight > 0 or cfg.crf_weight > 0:
             feats_f = feats.float() * (m3.view(B, E, 1, 1) if (cfg.dropout and m3 is not None) else 1.0)
             if cfg.rec_weight > 0:
-                rec_loss = -(norm(self.decoder(code)) * norm(feats_f)).sum(1).mean()
+                rec_loss = -pixel_cosine(self.decoder(code), feats_f).mean()
                 self.log('loss/rec', rec_loss)
                 loss = loss + cfg.rec_weight * rec_loss
             if cfg.aug_alignment_weight > 0:
                 _, code_aug = net(batch["img_aug"])
                 coord = F.interpolate(batch["coord_aug"].permute(0, 3, 1, 2), code_aug.shape[2], mode="bilinear",
                                       align_corners=False).permute(0, 2, 3, 1)
-                aug = -torch.einsum("bkhw,bkhw->bhw", norm(sample(code, coord)), norm(code_aug)).mean()
+                aug = -pixel_cosine(sample(code, coord), code_aug).mean()
                 self.log('loss/aug_alignment', aug)
                 loss = loss + cfg.aug_alignment_weight * aug
             if cfg.crf_weight > 0:

@@ -153,3 +153,18 @@ def test_crf_oracle_lattice_and_mean_field_sanity():
     lat = CO.Permutohedral((rng.random((3, 200)) * 4).astype(np.float32))
     x, y = rng.random((200, 1)).astype(np.float32), rng.random((200, 1)).astype(np.float32)
     assert abs((lat.compute(x) * y).sum() - (x * lat.compute(y, reverse=True)).sum()) < 1e-2 * abs((lat.compute(x) * y).sum())
+
+
+def test_contrastive_crf_loss_golden():
+    """oracle.contrastive_crf_loss against the reference's ContrastiveCRFLoss (modules.py:437-469) run by make_golden.py."""
+    g = _load("contrastive_crf_loss.pt")
+    torch.manual_seed(51)
+    gd = torch.rand(2, 3, 56, 56) * 4 - 2
+    cl = torch.nn.functional.normalize(torch.randn(2, 70, 56, 56), dim=1).requires_grad_(True)
+    torch.manual_seed(52)
+    coords = torch.cat([torch.randint(0, 56, size=[1, 300]), torch.randint(0, 56, size=[1, 300])], 0)
+    out = O.contrastive_crf_loss(gd, cl, coords, .5, .15, .05, 10.0, 3.0, 0.00)
+    grad, = torch.autograd.grad(out.mean(), cl)
+    assert torch.allclose(out.detach().reshape(-1)[::97], g["out_sub"], atol=1e-6)
+    assert abs(out.detach().abs().sum().item() - g["out_abs_sum"].item()) < 1e-5 * g["out_abs_sum"].item()
+    assert torch.allclose(grad.reshape(-1)[::53], g["grad_sub"], atol=1e-9, rtol=1e-5)
