@@ -571,6 +571,7 @@ def run_c4(args, rank, world, local):
         return ms.item()
 
     run(args.warmup, False)
+    model.check_update_health()  # N > 1: every rank made every peer-memory rendezvous of the warm-up
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -671,6 +672,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: fused peer-memory all-reduce + Adam (default) or NCCL all-reduce + Adam launches")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--sustain-seconds", type=float, default=5.0, help="length of the extra sustained-clock run (0 = skip)")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
@@ -734,7 +737,7 @@ def main():
     from stego_b200 import _lib
     from stego_b200.config import make_cfg
     from stego_b200.segmenter import LitUnsupervisedSegmenter
-    cfg = make_cfg(model_type=model_type, res=res, batch_size=B, random_backbone_init=True)
+    cfg = make_cfg(model_type=model_type, res=res, batch_size=B, random_backbone_init=True, p2p_update=args.exchange == "p2p")
     torch.manual_seed(0)  # seed_everything(0) on every rank, like the reference (train_segmentation.py:403)
     model = LitUnsupervisedSegmenter(N_CLASSES, cfg).to(dev)
     model.train()
@@ -810,6 +813,7 @@ def main():
             for i in range(nsteps):
                 model.training_step(batch, i)
             host_ms[0] = (time.perf_counter() - t_host) * 1e3 / max(nsteps, 1)  # CPU time to ENQUEUE one step
+        model.flush()  # the last step's parameter update (side stream) belongs to the timed region too
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -818,6 +822,7 @@ def main():
         return ms.item()
 
     run(args.warmup, False)
+    model.check_update_health()  # N > 1: every rank made every peer-memory rendezvous of the warm-up
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -869,8 +874,12 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": img_per_step, "per_gpu_batch": B, "res": res,
-                   "parallelism": f"dp{world}", "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; "
-                                                      "no explicit flush between steps"},
+                   "parallelism": f"dp{world}",
+                   "exchange": ("none (1 GPU)" if world == 1 else
+                                "all-reduce fused into Adam over NVLink peer memory (csrc/p2p_update.cu), on the side stream under "
+                                "the next step's backbone" if getattr(model, "_peer", None) is not None else
+                                "NCCL all-reduce + 3 Adam launches on the side stream"),
+                   "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush between steps"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_of(host_compact), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
                 "inputs": "LitUnsupervisedSegmenter.training_step with pinned-host bf16 images + uint8 labels (255 = "

@@ -276,6 +276,26 @@ STEGO_API int stego_cosine_bwd(const float* a, long long a_sb, long long a_sc, l
                                float eps, const float* cosv, const float* inva, const float* invb, const float* grad_cos,
                                float* da, float* db, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory: gradient all-reduce fused into the Adam update (replaces the DDP
+ * all-reduce behind manual_backward + the three optimizer.step() calls, src/train_segmentation.py:227-230, 476).
+ * Every rank allocates one peer-visible block [export 2 x n_pad floats | flags world x uint32], exchanges the 64-byte CUDA
+ * IPC handles out of band (the host does it over torch.distributed) and opens the other ranks' blocks. */
+STEGO_API int stego_p2p_alloc(long long bytes, long long* ptr_out, unsigned char* handle_out);
+STEGO_API int stego_p2p_open(const unsigned char* handle, long long* ptr_out);
+STEGO_API int stego_p2p_close(long long ptr);
+STEGO_API int stego_p2p_free(long long ptr);
+/* Copy the local flat gradient into export_slot (= this rank's export[epoch & 1]), store `epoch` into flags[rank] of every
+ * rank's block (peer_flags: host array of `world` addresses) and wait until every rank has published `epoch`.  The wait is
+ * one 32-thread CTA without shared memory.  status (device int) is set to 1 on time-out. */
+STEGO_API int stego_p2p_publish(const float* grad, long long n, float* export_slot, const long long* peer_flags, int rank,
+                                int world, int epoch, int* status, int timeout_ms, void* stream);
+/* grad[i] = sum over ranks r = 0..world-1 (fixed order) of peer_exports[r][i], read from peer memory; then torch.optim.Adam
+ * (amsgrad off, weight decay 0) with grad * grad_scale on every group.  group_desc: ngroups x 7 doubles
+ * (start, numel, lr, beta1, beta2, eps, 1-based step). */
+STEGO_API int stego_p2p_adam(const long long* peer_exports, int world, float* param, float* grad, float* exp_avg,
+                             float* exp_avg_sq, long long n, const double* group_desc, int ngroups, float grad_scale,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ _CTYPES = {
     "const char*": ctypes.c_char_p,
     "unsigned char*": ctypes.c_void_p,
     "const unsigned char*": ctypes.c_void_p,
+    "const double*": ctypes.c_void_p,
 }
 
 

@@ -21,6 +21,8 @@ TRAIN_DEFAULTS = dict(
     # stego_b200 execution switches (not in the reference config; read with getattr(..., default) by the modules)
     cuda_graph=True,   # replay the frozen ViT as one CUDA graph per input shape
     fused_step=True,   # hand-scheduled training step (fused_step.py) instead of the autograd-stitched one
+    overlap_update=True,  # parameter update on the side stream under the next step's backbone
+    p2p_update=True,   # N > 1: gradient all-reduce fused into Adam over NVLink peer memory (NCCL all-reduce as the fallback)
 )
 
 

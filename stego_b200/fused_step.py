@@ -315,11 +315,7 @@ class FusedStep:
             tail_done.record(main)
             self.side.wait_event(tail_done)
             with torch.cuda.stream(self.side):
-                from .segmenter import allreduce_gradients
-                allreduce_gradients(seg._flat)
-                net_optim.step()
-                cluster_probe_optim.step()
-                linear_probe_optim.step()
+                seg.apply_update()
                 if cfg.reset_probe_steps is not None and seg.global_step == cfg.reset_probe_steps:
                     seg.reset_probes()
                 self.update_done = torch.cuda.Event()

@@ -273,7 +273,7 @@ class LitUnsupervisedSegmenter(nn.Module):
             self._fused.flush()
 
     def state_dict(self, *args, **kwargs):
-        self.flush()
+        self.check_update_health()
         return super().state_dict(*args, **kwargs)
 
     def reset_probes(self):
@@ -300,10 +300,38 @@ class LitUnsupervisedSegmenter(nn.Module):
         self.flush()
         self._flat = FlatParams(groups, [self.cfg.lr, 5e-3, 5e-3])
         import torch.distributed as dist
+        self._peer = None
         if self._flat.param.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             # Lightning-DDP broadcasts module state from rank 0 when it wraps the model (train_segmentation.py:476)
             dist.broadcast(self._flat.param, src=0)
+            if getattr(self.cfg, "p2p_update", True):
+                # the per-step exchange: all-reduce fused into Adam over NVLink peer memory (csrc/p2p_update.cu); NCCL is
+                # the fallback when the ranks cannot map each other's memory (not one node, no P2P, IPC unavailable)
+                from .p2p import PeerUpdate
+                try:
+                    self._peer = PeerUpdate(self._flat)
+                except RuntimeError as e:
+                    if dist.get_rank() == 0:
+                        print(f"stego_b200: peer-memory update unavailable, using NCCL all-reduce ({e})")
         return tuple(self._flat.optimizers)
+
+    def apply_update(self):
+        """manual_backward's DDP all-reduce + the three optimizer.step() calls (train_segmentation.py:227-230) on the
+        current stream: one fused exchange-and-Adam over peer memory, or NCCL all-reduce + three Adam launches."""
+        net_optim, linear_probe_optim, cluster_probe_optim = self.optimizers()
+        if getattr(self, "_peer", None) is not None:
+            self._peer.step((net_optim, linear_probe_optim, cluster_probe_optim))
+        else:
+            allreduce_gradients(self._flat)
+            net_optim.step()
+            cluster_probe_optim.step()
+            linear_probe_optim.step()
+
+    def check_update_health(self):
+        """Raises if a rank missed the peer-memory rendezvous (synchronises the device)."""
+        self.flush()
+        if getattr(self, "_peer", None) is not None:
+            self._peer.check()
 
     def optimizers(self):
         if self._flat is None:
@@ -428,10 +456,7 @@ class LitUnsupervisedSegmenter(nn.Module):
         loss.backward()  # manual_backward (:227)
         self._flat.rebind()
         self._mark("backward")
-        allreduce_gradients(self._flat)
-        net_optim.step()
-        cluster_probe_optim.step()
-        linear_probe_optim.step()
+        self.apply_update()
         self._mark("allreduce_adam")
 
         if cfg.reset_probe_steps is not None and self.global_step == cfg.reset_probe_steps:

@@ -5,8 +5,9 @@ Lightning-DDP, src/train_segmentation.py:476 — per-rank local statistics, mean
 
   1. BEFORE the process group exists, every rank runs the single-GPU hand-scheduled step once per shard (all W shards,
      sequentially, fresh model each, identical seeds) and keeps each shard's gradients  -> mean over shards.
-  2. Then the process group is initialised and the SAME step runs data-parallel: rank r gets shard r, the one NCCL
-     all-reduce of the flat gradient buffer happens inside training_step (side stream), Adam consumes grad/W.
+  2. Then the process group is initialised and the SAME step runs data-parallel: rank r gets shard r, the exchange of the
+     flat gradient buffer happens inside training_step (side stream) — by default the fused peer-memory all-reduce + Adam
+     kernel (csrc/p2p_update.cu), with STEGO_TEST_P2P=0 one NCCL all-reduce + three Adam launches — Adam consumes grad/W.
   3. Compared on every rank: all-reduced gradient / W == mean of the shard gradients; parameters after the update ==
      torch-Adam arithmetic on that mean; parameters identical across ranks (all-gather); two more steps keep the ranks
      bit-identical (the replicas never drift).
@@ -47,13 +48,17 @@ def main():
 
     # ---- 2. the data-parallel step
     dist.init_process_group("nccl", device_id=dev)
-    model, _ = make_model(arch, dev, fused=True, seed=0)
+    want_p2p = os.environ.get("STEGO_TEST_P2P", "1") == "1"
+    model, _ = make_model(arch, dev, fused=True, seed=0, p2p_update=want_p2p)
+    # the exchange under test: the fused peer-memory all-reduce + Adam kernel (default) or the NCCL fallback
+    exchange = "p2p" if getattr(model, "_peer", None) is not None else "nccl"
     torch.manual_seed(777)
     loss = model.training_step(shards[rank], 0)
     g = grads_of(model)  # flat buffer after the SUM all-reduce
     p1 = params_of(model)
-    res_ = dict(rank=rank, world=world, loss=float(loss), grad_scale=model._flat.grad_scale)
+    res_ = dict(rank=rank, world=world, exchange=exchange, loss=float(loss), grad_scale=model._flat.grad_scale)
     ok = abs(model._flat.grad_scale - 1.0 / world) < 1e-12
+    ok &= exchange == ("p2p" if want_p2p else "nccl")
     worst_g, worst_p = 0.0, 0.0
     for k in NAMES:
         e = rel(g[k] / world, mean_g[k])
@@ -82,6 +87,7 @@ def main():
     ok &= identical
     res_.update(grad_rel_vs_shard_mean=worst_g, param_delta_rel_vs_adam_on_mean=worst_p,
                 replicas_bit_identical_after_3_steps=identical, ok=bool(ok))
+    model.check_update_health()  # raises if a rank missed the peer-memory rendezvous
     print("DDP_NCCL_RESULT " + json.dumps(res_), flush=True)
     dist.barrier()
     dist.destroy_process_group()
