@@ -213,9 +213,10 @@ def reference_step_fn(model_type, res, batch, device, autocast=False):
         return None
     import tempfile
     from stego_b200.config import make_cfg
+    import contextlib
     ts = H.load_reference_segmenter("reference")
-    with tempfile.TemporaryDirectory() as td:
-        ck = os.path.join(td, "dino.pth")
+    with tempfile.TemporaryDirectory() as td, contextlib.redirect_stdout(sys.stderr):  # the reference prints to stdout;
+        ck = os.path.join(td, "dino.pth")                                              # stdout carries ONE JSON line
         H.write_random_dino_checkpoint(ck, model_type, seed=0, perturb=False)
         cfg = make_cfg(model_type=model_type, res=res, batch_size=batch, pretrained_weights=ck)
         torch.manual_seed(0)
@@ -934,10 +935,25 @@ def main():
         line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()
                                if kk in ("ms", "tflops", "gbs", "share_of_step")} for k, v in ks.items()}
     if not args.no_cpu_baseline:
-        v, dt, cores, nst = time_cpu(model_type, res, 2, 3, 1, budget_s=30.0)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"{nst} steps of batch 2 of the {args.config} workload with the oracle port "
-                                          f"(full step incl. 2x ViT fwd) on {cores} host threads"}
+        # the reference's own training_step on the host cores when its copy travelled with the repo (baseline/_ref, made by
+        # __graft_entry__.build()); the oracle port otherwise
+        sample_b = {"c1": 4, "c2": 2, "c3": 1}.get(args.config, 2)
+        try:
+            r = time_reference_cpu(model_type, res, sample_b, 2, 0, budget_s=30.0)
+        except Exception as ex:  # the baseline must never take the bench line down
+            sys.stderr.write(f"cpu_baseline: reference step failed ({ex!r}); timing the oracle port instead\n")
+            r = None
+        if r is not None:
+            v, dt, cores, nst = r
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "reference",
+                                    "sample": f"{nst} steps of batch {sample_b} of the {args.config} workload: the reference's "
+                                              f"LitUnsupervisedSegmenter.training_step (baseline/_ref, unmodified; Lightning / "
+                                              f"Hydra stubbed) on {cores} host threads"}
+        else:
+            v, dt, cores, nst = time_cpu(model_type, res, 2, 3, 1, budget_s=30.0)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{nst} steps of batch 2 of the {args.config} workload with the oracle port "
+                                              f"(full step incl. 2x ViT fwd) on {cores} host threads"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
