@@ -919,7 +919,7 @@ def main():
                             "algorithmic_bytes_per_launch": d["bytes"],
                             "algorithmic_flops_per_launch": d["flops"], "ms_per_launch": d["ms"],
                             "share_of_step": d["share_of_step"], "peak_source": peaks["source"] + ", burst"}
-        if dom == "attention" and clocks.get("sm_mhz"):
+        if dom == "attention" and (clocks or {}).get("sm_mhz") and "exp_per_launch" in d:
             # second ceiling of this kernel: the MUFU pipe (16 ex2 / clk / SM at the clock sampled during the run)
             mufu_peak = 16.0 * d["sm_count"] * clocks["sm_mhz"] * 1e6 / 1e9  # Gexp/s
             line["roofline"]["mufu"] = {"exp_per_launch": d["exp_per_launch"], "achieved_gexp_s": d["exp_rate_gexp_s"],
