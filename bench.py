@@ -648,7 +648,7 @@ def run_c4(args, rank, world, local):
                          "frac": gbs / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": by,
                          "peak_source": peaks["source"]},
             **({"eval_pipeline": pipe} if pipe else {})}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import stego_oracle as O
         cc = torch.randn(1, C, h, w)
@@ -934,7 +934,7 @@ def main():
                                  "bound": "hbm/latency (S=121: intensity << ridge, SURVEY.md §8d)"}
         line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()
                                if kk in ("ms", "tflops", "gbs", "share_of_step")} for k, v in ks.items()}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
         # the reference's own training_step on the host cores when its copy travelled with the repo (baseline/_ref, made by
         # __graft_entry__.build()); the oracle port otherwise
         sample_b = {"c1": 4, "c2": 2, "c3": 1}.get(args.config, 2)
