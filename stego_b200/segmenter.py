@@ -10,8 +10,9 @@ batch_idx)` and `configure_optimizers()`; state-dict keys match the reference ch
   * the head, the correspondence loss, both probes and their backward are the fused kernels of
     modules.py / corr.py (autograd only stitches ~10 custom nodes together);
   * all trainable parameters (and their .grad) are views into ONE flat fp32 buffer, so data-parallel
-    training needs exactly one NCCL all-reduce per step (reference: Lightning-DDP bucketed all-reduce,
-    train_segmentation.py:476,227) and the three Adam optimisers are three launches of one fused kernel.
+    training needs exactly one exchange per step (reference: Lightning-DDP bucketed all-reduce,
+    train_segmentation.py:476,227): the sum over ranks is read from the peers' HBM over NVLink inside the Adam
+    kernel itself (p2p.py / csrc/p2p_update.cu), with one NCCL all-reduce + three Adam launches as the fallback.
 
 Per-rank semantics follow the reference: negatives, `old_mean` and every mean are computed over the LOCAL
 shard; only gradients cross ranks (averaged).
