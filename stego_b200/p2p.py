@@ -14,7 +14,10 @@ import torch
 
 from . import _lib
 
-TIMEOUT_MS = 10_000  # a peer that does not publish its gradient within 10 s: status flag, RuntimeError at the next flush()
+# A peer that does not publish its gradient within this time sets the status flag (RuntimeError at the next health check)
+# instead of hanging the GPU.  Generous on purpose: the first steps of a run (graph capture, lazy module loads) can skew the
+# ranks by seconds, and the waiting CTA is 32 sleeping threads.
+TIMEOUT_MS = 60_000
 
 
 class PeerUpdate:
