@@ -402,7 +402,7 @@ def kernel_rooflines(cfgd, peaks, dev):
     out["attention"] = dict(ms=ms, tflops=fl / ms / 1e9, gbs=(M * 4 * E * 2) / ms / 1e6, flops=fl, bytes=M * 4 * E * 2,
                             launches_per_step=12)
     # head-dim-64 attention needs one exponential per 256 tensor flops; MUFU.EX2 issues 16 / clk / SM, so the exponentials
-    # alone cap the kernel at half the bf16 tensor peak (profiles/r2_attention_v3.md).  Tile-padded count: 128-row query
+    # alone cap the kernel at 4096 flop/clk/SM, half the nominal tensor rate (profiles/r2_attention_v3.md).  Tile-padded count: 128-row query
     # tiles x 64-key tiles, what the kernel actually evaluates.
     n_exp = float(B2 * heads) * (-(-N // 128) * 128) * (-(-N // 64) * 64)
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -925,7 +925,7 @@ def main():
             line["roofline"]["mufu"] = {"exp_per_launch": d["exp_per_launch"], "achieved_gexp_s": d["exp_rate_gexp_s"],
                                         "peak_gexp_s": mufu_peak, "frac": d["exp_rate_gexp_s"] / mufu_peak,
                                         "note": "head_dim 64: 256 tensor flop per exponential, so the MUFU pipe caps this kernel at "
-                                                "0.5 of the bf16 tensor peak; frac here = share of that second ceiling"}
+                                                "4096 flop/clk/SM (1.19 PFLOP/s at 1965 MHz, half the nominal tensor rate); frac here = share of that second ceiling"}
         c = ks["corr_loss_fwd"]
         line["corr_roofline"] = {"kernel": "corr_loss_fwd (fd+cd einsums + loss reduction, 7 calls x B images)",
                                  "ms_per_launch": c["ms"], "achieved_tflops": c["tflops"],
