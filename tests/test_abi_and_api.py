@@ -146,3 +146,54 @@ def test_unsupervised_metrics_match_reference_arithmetic():
     ex = UnsupervisedMetrics("ex/", n, 2, True)
     ex.update(preds, target)
     assert ex.stats.shape == (n + 2, n) and "ex/mIoU" in ex.compute()
+
+
+def test_knn_file_helpers_round_trip(tmp_path):
+    """src/precompute_knns.py:66-67,94 / src/data.py:503-511: file name pattern and the `nns` key of the .npz."""
+    import numpy as np
+    from stego_b200.knn import nns_file_name, save_nns
+    name = nns_file_name("vit_small", "cocostuff27", "train", "five", 224)
+    assert name == "nns_vit_small_cocostuff27_train_five_224.npz"
+    nns = torch.arange(60, dtype=torch.int32).reshape(2, 30)
+    save_nns(str(tmp_path / name), nns)
+    back = np.load(tmp_path / name)
+    assert list(back.keys()) == ["nns"] and back["nns"].dtype == np.int64
+    assert (back["nns"] == nns.numpy()).all()
+
+
+def test_crf_host_helpers():
+    """Host-side pieces of the dense-CRF drop-in that need no GPU: lattice key packing (bits = 60 // d per coordinate,
+    negative coordinates included) and the image preparation of src/crf.py:23 against the oracle's."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import crf_oracle as CO
+    from stego_b200 import crf
+    g = torch.Generator().manual_seed(0)
+    for d in (2, 5):
+        bits = 60 // d
+        lim = 1 << (bits - 2)
+        coords = torch.randint(-lim, lim, (1000, d), generator=g)
+        keys = crf._pack(coords, d, bits)
+        assert torch.equal(crf._unpack(keys, d, bits), coords)
+        assert keys.unique().numel() == torch.unique(coords, dim=0).shape[0]
+        # the packed order is the lexicographic order of the coordinates (what searchsorted relies on)
+        order = torch.argsort(keys)
+        srt = coords[order]
+        as_tuples = [tuple(r.tolist()) for r in srt]
+        assert as_tuples == sorted(as_tuples)
+    img = torch.randn(3, 17, 23, generator=g)
+    got = crf.prepare_image(img)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (17, 23, 3)
+    assert (got.numpy() == CO.prepare_image(img)).all()
+
+
+def test_refused_without_cuda_for_new_entry_points():
+    """The round-2 entry points keep the no-CPU-fallback rule."""
+    from stego_b200 import crf
+    from stego_b200.modules import ContrastiveCRFLoss, pixel_cosine
+    with pytest.raises(RuntimeError):
+        crf.dense_crf(torch.randn(3, 8, 8), torch.randn(4, 8, 8))
+    with pytest.raises(RuntimeError):
+        ContrastiveCRFLoss(16, .5, .15, .05, 10.0, 3.0, 0.0)(torch.rand(1, 3, 8, 8), torch.rand(1, 5, 8, 8))
+    with pytest.raises(RuntimeError):
+        pixel_cosine(torch.randn(1, 4, 3, 3), torch.randn(1, 4, 3, 3))
