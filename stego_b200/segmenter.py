@@ -249,6 +249,13 @@ class LitUnsupervisedSegmenter(nn.Module):
         self.cluster_probe = ClusterLookup(dim, n_classes + cfg.extra_clusters)
         self.linear_probe = nn.Conv2d(dim, n_classes, (1, 1))
         self.decoder = nn.Conv2d(dim, self.net.n_feats, (1, 1))
+        # train_segmentation.py:80-88: the validation / test metric objects the eval script reads (`test_*_metrics`,
+        # eval_segmentation.py:137-141).  Their `stats` histograms are what the fused eval kernel accumulates into.
+        from .eval import UnsupervisedMetrics
+        self.cluster_metrics = UnsupervisedMetrics("test/cluster/", n_classes, cfg.extra_clusters, True)
+        self.linear_metrics = UnsupervisedMetrics("test/linear/", n_classes, 0, False)
+        self.test_cluster_metrics = UnsupervisedMetrics("final/cluster/", n_classes, cfg.extra_clusters, True)
+        self.test_linear_metrics = UnsupervisedMetrics("final/linear/", n_classes, 0, False)
         self.linear_probe_loss_fn = torch.nn.CrossEntropyLoss()
         self.crf_loss_fn = ContrastiveCRFLoss(cfg.crf_samples, cfg.alpha, cfg.beta, cfg.gamma, cfg.w1, cfg.w2, cfg.shift)
         self.contrastive_corr_loss_fn = ContrastiveCorrelationLoss(cfg)
@@ -265,6 +272,16 @@ class LitUnsupervisedSegmenter(nn.Module):
     def forward(self, x):
         self.flush()
         return self.net(x)[1]
+
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()` / `.cuda()`: the metric histograms are plain tensors (the reference's are torchmetrics states) and follow
+        the module to its device."""
+        out = super()._apply(fn, *args, **kwargs)
+        for name in ("cluster_metrics", "linear_metrics", "test_cluster_metrics", "test_linear_metrics"):
+            m = getattr(self, name, None)
+            if m is not None:
+                m.stats = fn(m.stats)
+        return out
 
     def flush(self):
         """The hand-scheduled step leaves its parameter update (all-reduce + Adam) on a side stream so that the next

@@ -197,3 +197,16 @@ def test_refused_without_cuda_for_new_entry_points():
         ContrastiveCRFLoss(16, .5, .15, .05, 10.0, 3.0, 0.0)(torch.rand(1, 3, 8, 8), torch.rand(1, 5, 8, 8))
     with pytest.raises(RuntimeError):
         pixel_cosine(torch.randn(1, 4, 3, 3), torch.randn(1, 4, 3, 3))
+
+
+def test_segmenter_carries_reference_metric_objects():
+    """train_segmentation.py:80-88: cluster / linear metric objects (validation and final) exist under the reference's names,
+    add nothing to the state dict (torchmetrics states are non-persistent) and follow the module across `.to()`."""
+    from stego_b200.config import make_cfg
+    from stego_b200.segmenter import LitUnsupervisedSegmenter
+    m = LitUnsupervisedSegmenter(27, make_cfg(random_backbone_init=True, extra_clusters=3))
+    assert m.cluster_metrics.prefix == "test/cluster/" and m.test_linear_metrics.prefix == "final/linear/"
+    assert tuple(m.test_cluster_metrics.stats.shape) == (30, 27) and tuple(m.linear_metrics.stats.shape) == (27, 27)
+    assert not [k for k in m.state_dict() if "metrics" in k]
+    m = m.to("meta")
+    assert m.test_cluster_metrics.stats.device.type == "meta" and m.test_cluster_metrics.stats.dtype == torch.int64
