@@ -14,7 +14,8 @@ densecrf.cpp, pairwise.cpp, permutohedral.cpp).  This file restates that PUBLISH
 
 Because no pydensecrf binary, source or golden vector is available offline, bit parity with the reference's CRF cannot be
 claimed; tests compare the CUDA implementation with THIS restatement (same lattice, fp32) by label agreement and by the
-marginals, and check the filter itself against brute-force Gaussian filtering.
+marginals, and check the restatement itself against brute-force Gaussian filtering and against an exact O(N^2) dense
+mean-field with the same conventions (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 
