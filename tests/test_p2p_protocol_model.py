@@ -7,7 +7,7 @@ The kernels implement, per rank r and step e = 1, 2, ... on one in-order stream:
     adam(e)      read export_p[e & 1] for every rank p       (must see step e's gradient of every rank)
 DESIGN.md §6 claims the double buffer makes a second barrier unnecessary: nobody overwrites a slot a peer may still read.
 This test explores EVERY interleaving of the ranks' operations (each store / each read its own atomic event) for 2 ranks x 8
-steps, 3 ranks x 3 steps and 4 ranks x 2 steps and asserts that every read returns the epoch it expects — and that the same protocol with a
+steps, 3 ranks x 3 steps and 4 ranks x 3 steps and asserts that every read returns the epoch it expects — and that the same protocol with a
 single export buffer is caught violating it, so the check has teeth.
 """
 from collections import deque
@@ -66,7 +66,7 @@ def _explore(world, steps, slots):
 
 
 def test_double_buffered_exchange_is_safe_under_every_interleaving():
-    for world, steps in ((2, 8), (3, 3), (4, 2)):
+    for world, steps in ((2, 8), (3, 3), (4, 3)):
         violations, finals, states = _explore(world, steps, slots=2)
         assert violations == 0 and finals >= 1, (world, steps, violations, finals, states)
 
