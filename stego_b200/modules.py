@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 from os.path import join  # noqa: F401  (reference scripts rely on star-exported names)
 from typing import Optional
 
@@ -246,7 +247,7 @@ class DinoFeaturizer(nn.Module):
             msg = self.model.load_state_dict(sd, strict=False)
             print('Pretrained weights found at {} and loaded with msg: {}'.format(weights, msg))
         elif getattr(cfg, "random_backbone_init", False):
-            print("DinoFeaturizer: keeping the random ViT initialisation (cfg.random_backbone_init).")
+            print("DinoFeaturizer: keeping the random ViT initialisation (cfg.random_backbone_init).", file=sys.stderr)
         else:
             print("Since no pretrained weights have been provided, we load the reference pretrained DINO weights.")
             sd = torch.hub.load_state_dict_from_url(url="https://dl.fbaipublicfiles.com/dino/" + self._URLS[(arch, self.patch_size)])
