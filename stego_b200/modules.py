@@ -687,6 +687,16 @@ class ContrastiveCRFLoss(nn.Module):
                           torch.randint(0, w, size=[1, self.n_samples], device=device)], 0)
 
     def forward_with_coords(self, guidance, clusters, coords):
+        """The loss for caller-supplied sample positions (int64 [2, n]: row indices, column indices).  The kernels index
+        with them unchecked, so they are validated here (one device sync; `forward` draws them in range and skips this)."""
+        h, w = guidance.shape[2], guidance.shape[3]
+        if coords.dim() != 2 or coords.shape[0] != 2 or coords.dtype != torch.long:
+            raise ValueError("ContrastiveCRFLoss: coords must be an int64 [2, n] tensor")
+        if bool(((coords[0] < 0) | (coords[0] >= h) | (coords[1] < 0) | (coords[1] >= w)).any()):
+            raise ValueError("ContrastiveCRFLoss: sample positions outside the feature map")
+        return self._apply_kernel(guidance, clusters, coords)
+
+    def _apply_kernel(self, guidance, clusters, coords):
         return _CrfLossFn.apply(guidance, clusters, coords, self.alpha, self.beta, self.gamma, self.w1, self.w2, self.shift)
 
     def forward(self, guidance, clusters):
@@ -695,4 +705,4 @@ class ContrastiveCRFLoss(nn.Module):
         assert guidance.shape[0] == clusters.shape[0]
         assert guidance.shape[2:] == clusters.shape[2:]
         coords = self.draw_coords(guidance.shape[2], guidance.shape[3], clusters.device)
-        return self.forward_with_coords(guidance, clusters, coords)
+        return self._apply_kernel(guidance, clusters, coords)

@@ -197,6 +197,12 @@ def test_refused_without_cuda_for_new_entry_points():
         ContrastiveCRFLoss(16, .5, .15, .05, 10.0, 3.0, 0.0)(torch.rand(1, 3, 8, 8), torch.rand(1, 5, 8, 8))
     with pytest.raises(RuntimeError):
         pixel_cosine(torch.randn(1, 4, 3, 3), torch.randn(1, 4, 3, 3))
+    # caller-supplied sample positions are validated before they reach the kernels
+    crf_loss = ContrastiveCRFLoss(4, .5, .15, .05, 10.0, 3.0, 0.0)
+    with pytest.raises(ValueError):
+        crf_loss.forward_with_coords(torch.rand(1, 3, 8, 8), torch.rand(1, 5, 8, 8), torch.tensor([[0, 1, 2, 8], [0, 1, 2, 3]]))
+    with pytest.raises(ValueError):
+        crf_loss.forward_with_coords(torch.rand(1, 3, 8, 8), torch.rand(1, 5, 8, 8), torch.zeros(2, 4, dtype=torch.int32))
 
 
 def test_segmenter_carries_reference_metric_objects():
