@@ -2,9 +2,11 @@
 its duration and the idle gap before it.  Unlike the ncu launch list this is warm and NOT serialised, so absolute
 times and gaps are meaningful (profiler overhead: a few % on a 6 ms step).
     python profiles/step_timeline.py [c1|c2] > gpurun_out/timeline.md
-Under torchrun (WORLD_SIZE > 1) every rank runs the data-parallel step over NCCL and rank 0 prints; the report then also
-says how much of the update (NCCL all-reduce + the three fused-Adam launches, side stream) is EXPOSED, i.e. not
-overlapped by any other kernel of the next step's frozen backbone.
+Under torchrun (WORLD_SIZE > 1) every rank runs the data-parallel step and rank 0 prints; the report then also says how
+much of the update (exchange + Adam, side stream) is EXPOSED, i.e. not overlapped by any other kernel of the next step's
+frozen backbone.  CAVEAT (measured at 8 ranks, round 2): the profiler start-up skews the ranks by tens of milliseconds, a
+collective kernel that waits for its peers inside the kernel (NCCL) then shows that skew as kernel time, and the EXPOSED
+figure is meaningless — use it at N = 1 / 2 only, and judge N = 8 by the step times of bench.py with both exchanges.
 """
 import os
 import sys
